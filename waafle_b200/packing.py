@@ -1,0 +1,131 @@
+"""CSR/SoA packing of contigs, loci and hits: the host side of the drop-in boundary.
+
+The reference keeps one `Contig` object per FASTA record holding lists of `Locus`
+and `Hit` objects (waafle/waafle_orgscorer.py:908-925, 943-953).  Here the same
+information is laid out as the flat arrays of `wfl_batch` (include/waafle_b200.h):
+contigs in FASTA order, loci in GFF order and hits in blastout order inside each
+contig (the reference's iteration orders: UT:255-270, UT:341-355).
+"""
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from .utils import die, say
+
+_ARRAYS = ["hit_off", "locus_off", "hit_qstart", "hit_qend", "hit_taxon", "hit_score",
+           "hit_scov", "hit_strand", "hit_sysmask", "locus_start", "locus_end", "locus_strand"]
+
+
+@dataclass
+class Batch:
+    hit_off: np.ndarray        # int64 [n+1]
+    locus_off: np.ndarray      # int64 [n+1]
+    hit_qstart: np.ndarray     # int32 [H]
+    hit_qend: np.ndarray       # int32 [H]
+    hit_taxon: np.ndarray      # int32 [H]  node index (taxonomy.Taxonomy.index)
+    hit_score: np.ndarray      # float64 [H] waafle_score
+    hit_scov: np.ndarray       # float64 [H] scov_modified
+    hit_strand: np.ndarray     # int8 [H]
+    locus_start: np.ndarray    # int32 [L]
+    locus_end: np.ndarray      # int32 [L]
+    locus_strand: np.ndarray   # int8 [L]
+    hit_sysmask: Optional[np.ndarray] = None   # uint32 [H]
+    # host-only side tables (never shipped to the device)
+    contig_names: list = field(default_factory=list)
+    contig_lengths: Optional[np.ndarray] = None
+    hit_row: Optional[np.ndarray] = None       # index of each packed hit in the HitTable
+    locus_row: Optional[np.ndarray] = None     # index of each packed locus in the LocusTable
+
+    @property
+    def n_contigs(self):
+        return len(self.hit_off) - 1
+
+    @property
+    def n_hits(self):
+        return int(self.hit_off[-1])
+
+    @property
+    def n_loci(self):
+        return int(self.locus_off[-1])
+
+    def arrays(self):
+        """Dict of the device-facing arrays (what the C ABI and the oracle consume)."""
+        return {k: getattr(self, k) for k in _ARRAYS if getattr(self, k) is not None}
+
+    def slice(self, c0, c1):
+        """Contigs [c0, c1) as an independent batch with rebased offsets."""
+        h0, h1 = int(self.hit_off[c0]), int(self.hit_off[c1])
+        l0, l1 = int(self.locus_off[c0]), int(self.locus_off[c1])
+        cut = lambda a, lo, hi: None if a is None else a[lo:hi]
+        return Batch(
+            hit_off=self.hit_off[c0:c1 + 1] - h0, locus_off=self.locus_off[c0:c1 + 1] - l0,
+            hit_qstart=self.hit_qstart[h0:h1], hit_qend=self.hit_qend[h0:h1],
+            hit_taxon=self.hit_taxon[h0:h1], hit_score=self.hit_score[h0:h1],
+            hit_scov=self.hit_scov[h0:h1], hit_strand=self.hit_strand[h0:h1],
+            locus_start=self.locus_start[l0:l1], locus_end=self.locus_end[l0:l1],
+            locus_strand=self.locus_strand[l0:l1], hit_sysmask=cut(self.hit_sysmask, h0, h1),
+            contig_names=self.contig_names[c0:c1],
+            contig_lengths=cut(self.contig_lengths, c0, c1),
+            hit_row=cut(self.hit_row, h0, h1), locus_row=cut(self.locus_row, l0, l1))
+
+    def algorithmic_bytes(self, n_systems=0):
+        """29 B/hit + 9 B/locus + 16 B/contig in, 40 + G(1+4S) B/contig out."""
+        return (29 * self.n_hits + 9 * self.n_loci + 16 * self.n_contigs
+                + 40 * self.n_contigs + self.n_loci * (1 + 4 * n_systems))
+
+
+def _group(names, index, what):
+    """Map row -> contig index; unknown contigs are warned about and dropped like OS:921-923."""
+    cid = np.fromiter((index.get(n, -1) for n in names), dtype=np.int64, count=len(names))
+    if len(cid):
+        starts = np.r_[True, names[1:] != names[:-1]]
+        for n in names[starts & (cid < 0)]:
+            say("  Unknown contig in <{}> file".format(what), n)
+    return cid
+
+
+def pack(contig_lengths, loci, hits, taxonomy):
+    """Pack parsed inputs. `taxonomy` must already be built with the hit taxa as extra names."""
+    names = list(contig_lengths)
+    index = {n: i for i, n in enumerate(names)}
+    n = len(names)
+
+    lc = _group(loci.seqname, index, "gff")
+    lrow = np.nonzero(lc >= 0)[0]
+    lrow = lrow[np.argsort(lc[lrow], kind="stable")]
+    locus_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(lc[lrow], minlength=n), out=locus_off[1:])
+
+    hc = _group(hits.qseqid, index, "blastout")
+    if len(hc):
+        # the reference assumes the blastout is grouped by query (UT:255-258)
+        starts = np.r_[True, hits.qseqid[1:] != hits.qseqid[:-1]]
+        blocks = hc[starts]
+        blocks = blocks[blocks >= 0]
+        if len(np.unique(blocks)) != len(blocks):
+            die("blastout is not grouped by query sequence")
+    hrow = np.nonzero(hc >= 0)[0]
+    hrow = hrow[np.argsort(hc[hrow], kind="stable")]
+    hit_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(hc[hrow], minlength=n), out=hit_off[1:])
+
+    taxon = np.fromiter((taxonomy.index[t] for t in hits.taxon[hrow]), dtype=np.int32,
+                        count=len(hrow))
+    return Batch(
+        hit_off=hit_off, locus_off=locus_off,
+        hit_qstart=np.ascontiguousarray(hits.qstart[hrow]),
+        hit_qend=np.ascontiguousarray(hits.qend[hrow]),
+        hit_taxon=taxon,
+        hit_score=np.ascontiguousarray(hits.score[hrow]),
+        hit_scov=np.ascontiguousarray(hits.scov_modified[hrow]),
+        hit_strand=np.ascontiguousarray(hits.strand[hrow]),
+        hit_sysmask=None if hits.sysmask is None or not hits.systems
+        else np.ascontiguousarray(hits.sysmask[hrow]),
+        locus_start=np.ascontiguousarray(loci.start[lrow]),
+        locus_end=np.ascontiguousarray(loci.end[lrow]),
+        locus_strand=np.ascontiguousarray(loci.strand[lrow]),
+        contig_names=names,
+        contig_lengths=np.array([contig_lengths[k] for k in names], dtype=np.int64),
+        hit_row=hrow, locus_row=lrow)
