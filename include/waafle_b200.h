@@ -1,0 +1,173 @@
+/*
+ * waafle_b200.h -- C ABI of the B200-native waafle_orgscorer engine.
+ *
+ * Drop-in boundary.  The reference has no FFI: the boundary is a code
+ * region, the body of the "major contig loop" of
+ *     /root/reference/waafle/waafle_orgscorer.py:952-960
+ * (Contig.attach_hits -> update_gene_scores -> [raise_taxonomy]* -> evaluate_contig) plus the
+ * state it leaves for write_main_output_files (waafle_orgscorer.py:838-890: best_one /
+ * best_two .ok/.crit/.rank/.clade1/.clade2/.synteny/.direction/.tails*, Locus.ignore,
+ * Locus.annotations).  A maintainer replaces that block by ONE wfl_score_batch call on the
+ * packed arrays below (INTEGRATION.md shows the ctypes binding).
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer (pageable or
+ * pinned); the engine owns device memory and its stream; every entry point returns 0 on
+ * success and a negative wfl_status on failure and never throws / aborts; wfl_last_error()
+ * gives the text.  One handle per GPU; a handle is not thread-safe, distinct handles are
+ * independent.  There is no CPU fallback: without a CUDA device wfl_create fails.
+ */
+#ifndef WAAFLE_B200_H
+#define WAAFLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFL_ABI_VERSION 1
+#define WFL_MAX_SYSTEMS 32
+
+typedef struct wfl_engine wfl_engine;
+
+typedef enum {
+    WFL_OK = 0,
+    WFL_ERR_ARG = -1,       /* bad argument / inconsistent batch            */
+    WFL_ERR_CUDA = -2,      /* CUDA runtime error (text in wfl_last_error)   */
+    WFL_ERR_STATE = -3,     /* params / taxonomy / batch not set             */
+    WFL_ERR_CAPACITY = -4,  /* caller-provided output buffer too small       */
+    WFL_ERR_RUNAWAY = -5    /* >100 taxonomy lifts (reference: wu.die, waafle_orgscorer.py:580-581) */
+} wfl_status;
+
+/* Engine-relevant CLI flags (waafle_orgscorer.py:188-296, waafle_genecaller.py:83-101;
+ * read inside the engine at waafle_orgscorer.py:338-346,351,362,365,367,413-420,497,
+ * 513-516,589,604,610,625-627,636,644-661,679-687,701,707,714,720-721,741). */
+typedef struct {
+    double k1;                    /* --one-clade-threshold                      */
+    double k2;                    /* --two-clade-threshold                      */
+    double range;                 /* --range                                    */
+    double ambiguous_fraction;    /* --ambiguous-fraction                       */
+    double min_overlap;           /* --min-overlap                              */
+    double min_scov;              /* --min-scov                                 */
+    double min_gene_length;       /* --min-gene-length                          */
+    int32_t disambiguate_one;     /* 0 report-best, 1 meld                      */
+    int32_t disambiguate_two;     /* 0 report-best, 1 jump, 2 meld              */
+    int32_t weak_loci;            /* 0 ignore, 1 penalize, 2 assign-unknown     */
+    int32_t ambiguous_threshold;  /* 0 off, 1 lenient, 2 strict                 */
+    int32_t sister_penalty;       /* 0 off, 1 lenient, 2 strict                 */
+    int32_t annotation_threshold; /* 0 off, 1 lenient, 2 strict                 */
+    int32_t allow_lca;            /* --allow-lca                                */
+    int32_t stranded;             /* --stranded                                 */
+    int32_t jump_taxonomy;        /* --jump-taxonomy, 0 = off                   */
+    int32_t clade_genes;          /* --clade-genes, -1 = off                    */
+    int32_t clade_leaves;         /* --clade-leaves, -1 = off                   */
+    int32_t n_systems;            /* annotation systems carried by hit_sysmask  */
+} wfl_params;
+
+/* One batch of contigs, CSR over contigs, SoA over hits and loci.
+ * Replaces the per-contig Hit / Locus object lists (waafle/utils.py:192-241, 298-322).
+ * Contigs in FASTA order, loci in GFF order (ALL loci; the engine applies
+ * --min-gene-length, waafle_orgscorer.py:350-352), hits in blastout order. */
+typedef struct {
+    int64_t n_contigs, n_hits, n_loci;
+    const int64_t *hit_off;        /* [n_contigs+1] */
+    const int64_t *locus_off;      /* [n_contigs+1] */
+    const int32_t *hit_qstart;     /* [n_hits] Hit.qstart                                */
+    const int32_t *hit_qend;       /* [n_hits] Hit.qend                                  */
+    const int32_t *hit_taxon;      /* [n_hits] node index of Hit.taxon                   */
+    const double  *hit_score;      /* [n_hits] Hit.waafle_score   (utils.py:229)         */
+    const double  *hit_scov;       /* [n_hits] Hit.scov_modified  (utils.py:227)         */
+    const int8_t  *hit_strand;     /* [n_hits] '+' or '-'         (utils.py:214)         */
+    const uint32_t *hit_sysmask;   /* [n_hits] bit s: hit annotates system s; NULL if n_systems==0 */
+    const int32_t *locus_start;    /* [n_loci] */
+    const int32_t *locus_end;      /* [n_loci] */
+    const int8_t  *locus_strand;   /* [n_loci] first byte of the GFF strand column */
+} wfl_batch;
+
+/* call codes */
+#define WFL_CALL_UNCLASSIFIED 0
+#define WFL_CALL_NO_LGT 1
+#define WFL_CALL_LGT 2
+/* locus_flags bits */
+#define WFL_LOCUS_RETAINED 1
+#define WFL_LOCUS_IGNORED 2
+
+/* Caller-allocated result buffers (capacities in elements; sizes returned in *_used).
+ * Replaces Contig.best_one / best_two, Locus.ignore and Locus.annotations. */
+typedef struct {
+    /* per contig [n_contigs] */
+    uint8_t *call;          /* WFL_CALL_*                                               */
+    uint8_t *direction;     /* 0 "A?B", 1 "B>A"       (waafle_orgscorer.py:485,543)     */
+    int32_t *lifts;         /* taxonomy lifts performed (jumps + loop)                  */
+    int32_t *clade1;        /* clade / clade_A after melding, -1 if unclassified        */
+    int32_t *clade2;        /* clade_B after melding, -1 unless lgt                     */
+    int32_t *lca;           /* LCA(clade_A, clade_B), -1 unless lgt                     */
+    int32_t *best1;         /* clade1 of the best option before melding                 */
+    int32_t *best2;
+    double  *crit;          /* min_score / min_max_score                                */
+    double  *rank;          /* avg_score / avg_max_score                                */
+    int64_t *member_off;    /* [n_contigs+1] CSR into members                           */
+    int32_t *n_members_a;   /* first n_members_a of a contig's members are side A       */
+    /* distinct melded clades (tails are derived on the host, waafle_orgscorer.py:750-759) */
+    int32_t *members;
+    int64_t members_capacity;
+    int64_t members_used;   /* out */
+    /* per raw locus [n_loci] */
+    uint8_t *synteny;       /* synteny character, 0 for dropped loci / unclassified     */
+    uint8_t *locus_flags;   /* WFL_LOCUS_*                                              */
+    int32_t *ann_winner;    /* [n_loci * n_systems] batch hit index or -1               */
+    /* on-device compaction: contig indices grouped lgt | no_lgt | unclassified */
+    int64_t *call_counts;   /* [3] = {n_lgt, n_no_lgt, n_unclassified}                  */
+    int64_t *call_index;    /* [n_contigs]                                              */
+} wfl_results;
+
+/* Counters of the last run (metrics / bench evidence). */
+typedef struct {
+    int64_t kernel_launches;    /* kernels launched by the last score/run call           */
+    int64_t contigs, hits, loci;
+    int64_t matched_pairs;      /* (hit, locus) matches                                  */
+    int64_t groups;             /* (clade, locus) envelopes integrated, all levels       */
+    int64_t levels;             /* sum over contigs of taxonomy levels evaluated         */
+    int64_t pairs_tested;       /* two-clade pairs mask-tested                           */
+    int64_t pairs_scored;       /* two-clade pairs that passed the mask test             */
+    int64_t workspace_retries;  /* contigs replayed with a larger workspace              */
+    int64_t smem_contigs;       /* contigs whose whole working set stayed in shared mem  */
+    float   ms_h2d, ms_kernels, ms_d2h, ms_score_kernel;   /* CUDA-event times         */
+} wfl_stats;
+
+int  wfl_abi_version(void);
+int  wfl_device_count(void);
+int  wfl_create(int device, wfl_engine **out);
+void wfl_destroy(wfl_engine *e);
+const char *wfl_last_error(const wfl_engine *e);
+
+int  wfl_set_params(wfl_engine *e, const wfl_params *p);
+/* Node index order must equal the Python str order of the clade names (so that
+ * `clade1 < clade2`, waafle_orgscorer.py:608, is an integer compare).  parent[root] == root;
+ * unlisted taxa have parent == root (utils.py:386-387), listed == 0, leaf_count == 1. */
+int  wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent,
+                      const int32_t *depth, const int32_t *leaf_count, const uint8_t *listed,
+                      int32_t root_idx, int32_t unknown_idx);
+
+/* Host buffers in, host buffers out: H2D + kernels + D2H (the plugin call; bench "e2e"). */
+int  wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out);
+
+/* Split form for device-resident timing (bench "value"): upload once, run many, download. */
+int  wfl_upload_batch(wfl_engine *e, const wfl_batch *in);
+int  wfl_run_resident(wfl_engine *e);
+int  wfl_download_results(wfl_engine *e, wfl_results *out);
+
+int  wfl_get_stats(const wfl_engine *e, wfl_stats *out);
+/* Tuning knobs (all optional): threads per CTA, dynamic shared memory bytes per CTA,
+ * CTAs per SM.  0 keeps the default. */
+int  wfl_configure(wfl_engine *e, int threads, int smem_bytes, int ctas_per_sm);
+
+/* Test hook: level-0 gene scores of one contig of the resident batch as COO triples
+ * (clade, retained-locus index, score); returns the number of triples or <0. */
+int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int32_t *locus,
+                              double *score, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAAFLE_B200_H */

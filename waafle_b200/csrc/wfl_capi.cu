@@ -1,0 +1,595 @@
+// C ABI of the engine (include/waafle_b200.h): handle, device memory, H2D / launch / D2H.
+// Plain CUDA runtime -- no torch types anywhere near the boundary.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "wfl_device.cuh"
+
+using namespace wfl;
+
+namespace {
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct wfl_engine {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string err;
+    bool have_params = false, have_tax = false, have_batch = false, have_results = false;
+    DevParams P{};
+    DevTax tax{};
+    DevBatch b{};
+    DevOut o{};
+    int64_t n = 0, nh = 0, nl = 0;
+    int S = 0;
+    // knobs
+    int threads = 128, smem_bytes = 36 * 1024, ctas_per_sm = 6;
+    size_t slab_bytes = 128 * 1024;
+    // device buffers (grow-only)
+    Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4];
+    wfl_stats stats{};
+    int64_t members_total = 0;
+};
+
+namespace {
+
+bool set_err(wfl_engine *e, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    e->err = buf;
+    return false;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t _err = (call);                                                        \
+        if (_err != cudaSuccess) {                                                        \
+            set_err(e, "%s failed: %s", #call, cudaGetErrorString(_err));                 \
+            return WFL_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+int ensure(wfl_engine *e, Buf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return WFL_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return WFL_OK;
+}
+
+template <class T>
+int upload(wfl_engine *e, Buf &b, const T *src, size_t n, const T **dst) {
+    int rc = ensure(e, b, n * sizeof(T));
+    if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    *dst = static_cast<const T *>(b.p);
+    return WFL_OK;
+}
+
+template <class T>
+int outbuf(wfl_engine *e, Buf &b, size_t n, T **dst) {
+    int rc = ensure(e, b, n * sizeof(T));
+    if (rc) return rc;
+    *dst = static_cast<T *>(b.p);
+    return WFL_OK;
+}
+
+int check_batch(wfl_engine *e, const wfl_batch *in) {
+    if (!in || in->n_contigs < 0 || in->n_hits < 0 || in->n_loci < 0) {
+        set_err(e, "bad batch sizes");
+        return WFL_ERR_ARG;
+    }
+    if (in->n_hits >= (1ll << 31) || in->n_loci >= (1ll << 31) || in->n_contigs >= (1ll << 31)) {
+        set_err(e, "batch too large: contigs, hits and loci must each be < 2^31 per batch");
+        return WFL_ERR_ARG;
+    }
+    if (!in->hit_off || !in->locus_off || (in->n_hits && (!in->hit_qstart || !in->hit_qend ||
+        !in->hit_taxon || !in->hit_score || !in->hit_scov || !in->hit_strand)) ||
+        (in->n_loci && (!in->locus_start || !in->locus_end || !in->locus_strand))) {
+        set_err(e, "null array in batch");
+        return WFL_ERR_ARG;
+    }
+    if (e->P.p.n_systems > 0 && in->n_hits && !in->hit_sysmask) {
+        set_err(e, "n_systems > 0 but hit_sysmask is null");
+        return WFL_ERR_ARG;
+    }
+    if (in->hit_off[0] != 0 || in->locus_off[0] != 0 || in->hit_off[in->n_contigs] != in->n_hits ||
+        in->locus_off[in->n_contigs] != in->n_loci) {
+        set_err(e, "CSR offsets do not span the hit / locus arrays");
+        return WFL_ERR_ARG;
+    }
+    for (int64_t c = 0; c < in->n_contigs; ++c)
+        if (in->hit_off[c + 1] < in->hit_off[c] || in->locus_off[c + 1] < in->locus_off[c]) {
+            set_err(e, "CSR offsets are not monotone at contig %lld", (long long)c);
+            return WFL_ERR_ARG;
+        }
+    for (int64_t h = 0; h < in->n_hits; ++h)
+        if ((uint32_t)in->hit_taxon[h] >= (uint32_t)e->tax.n_nodes) {
+            set_err(e, "hit %lld: taxon index %d outside the taxonomy", (long long)h, in->hit_taxon[h]);
+            return WFL_ERR_ARG;
+        }
+    return WFL_OK;
+}
+
+int alloc_outputs(wfl_engine *e) {
+    const size_t n = (size_t)e->n, nl = (size_t)e->nl, S = (size_t)e->S;
+    int rc = 0;
+    DevOut &o = e->o;
+    rc |= outbuf(e, e->out[0], n, &o.call);
+    rc |= outbuf(e, e->out[1], n, &o.direction);
+    rc |= outbuf(e, e->out[2], n, &o.lifts);
+    rc |= outbuf(e, e->out[3], n, &o.clade1);
+    rc |= outbuf(e, e->out[4], n, &o.clade2);
+    rc |= outbuf(e, e->out[5], n, &o.lca);
+    rc |= outbuf(e, e->out[6], n, &o.best1);
+    rc |= outbuf(e, e->out[7], n, &o.best2);
+    rc |= outbuf(e, e->out[8], n, &o.crit);
+    rc |= outbuf(e, e->out[9], n, &o.rank);
+    rc |= outbuf(e, e->out[10], nl, &o.synteny);
+    rc |= outbuf(e, e->out[11], nl, &o.locus_flags);
+    rc |= outbuf(e, e->out[12], nl * S, &o.ann_winner);
+    rc |= outbuf(e, e->out[13], n, &o.n_mem_a);
+    rc |= outbuf(e, e->out[14], n, &o.n_mem_b);
+    rc |= outbuf(e, e->out[15], n, &o.mem_pos);
+    rc |= outbuf(e, e->out[17], n, &o.status);
+    if (rc) return WFL_ERR_CUDA;
+    size_t pool = std::max<size_t>(e->out[16].cap / sizeof(int32_t), std::max<size_t>(2 * n, 1 << 16));
+    rc = outbuf(e, e->out[16], pool, &o.mem_pool);
+    o.mem_pool_cap = (int64_t)(e->out[16].cap / sizeof(int32_t));
+    return rc;
+}
+
+int run_kernels(wfl_engine *e) {
+    if (!e->have_params || !e->have_tax || !e->have_batch) {
+        set_err(e, "params, taxonomy and batch must be set before running");
+        return WFL_ERR_STATE;
+    }
+    int rc = alloc_outputs(e);
+    if (rc) return rc;
+    DevCounters *ctr;
+    if ((rc = outbuf(e, e->ctr, 1, &ctr))) return rc;
+    int64_t *cm_off, *cm_counts, *cm_index, *cm_totals, *scan_tmp;
+    int32_t *cm_na;
+    if ((rc = outbuf(e, e->cm[0], (size_t)e->n + 1, &cm_off))) return rc;
+    if ((rc = outbuf(e, e->cm[1], (size_t)e->n, &cm_na))) return rc;
+    if ((rc = outbuf(e, e->cm[2], 8, &cm_counts))) return rc;
+    if ((rc = outbuf(e, e->cm[3], (size_t)e->n, &cm_index))) return rc;
+    cm_totals = cm_counts + 4;
+    if ((rc = outbuf(e, e->scratch, compaction_scratch_elems(e->n), &scan_tmp))) return rc;
+
+    e->stats = wfl_stats{};
+    e->stats.contigs = e->n;
+    e->stats.hits = e->nh;
+    e->stats.loci = e->nl;
+    DevCounters hc{};
+    DevCounters acc{};
+    int grid = e->sm_count * e->ctas_per_sm;
+    size_t slab_bytes = e->slab_bytes;
+    const int64_t *work_list = nullptr;
+    int64_t n_work = e->n;
+    std::vector<int64_t> replay;
+    CU(cudaEventRecord(e->ev[1], e->stream));
+    for (int attempt = 0;; ++attempt) {
+        char *slab;
+        if ((rc = outbuf(e, e->slab, (size_t)grid * slab_bytes, &slab))) return rc;
+        CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
+        ScoreArgs a{};
+        a.b = e->b;
+        a.t = e->tax;
+        a.o = e->o;
+        a.P = e->P;
+        a.ctr = ctr;
+        a.work_list = work_list;
+        a.n_work = n_work;
+        a.slab = slab;
+        a.slab_bytes = slab_bytes;
+        a.smem_bytes = e->smem_bytes;
+        a.dbg_contig = -1;
+        if (n_work > 0) {
+            launch_score_kernel(a, (int)std::min<int64_t>(grid, n_work), e->threads, e->stream);
+            CU(cudaGetLastError());
+            e->stats.kernel_launches++;
+        }
+        if (attempt == 0) CU(cudaEventRecord(e->ev[2], e->stream));
+        CU(cudaMemcpyAsync(&hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        acc.matched_pairs += hc.matched_pairs;
+        acc.groups += hc.groups;
+        acc.levels += hc.levels;
+        acc.pairs_tested += hc.pairs_tested;
+        acc.pairs_scored += hc.pairs_scored;
+        acc.smem_contigs += hc.smem_contigs;
+        if (hc.n_runaway) {
+            set_err(e, "Runaway taxonomic recursion in %llu contig(s)", hc.n_runaway);
+            return WFL_ERR_RUNAWAY;
+        }
+        if ((int64_t)hc.mem_pool_used > e->o.mem_pool_cap) {
+            // melded-member staging pool too small: grow it and redo the whole batch
+            if (attempt > 8) { set_err(e, "member pool keeps overflowing"); return WFL_ERR_CUDA; }
+            Buf nb;
+            if ((rc = ensure(e, nb, (size_t)hc.mem_pool_used * sizeof(int32_t) * 2))) return rc;
+            cudaFree(e->out[16].p);
+            e->out[16] = nb;
+            e->o.mem_pool = static_cast<int32_t *>(nb.p);
+            e->o.mem_pool_cap = (int64_t)(nb.cap / sizeof(int32_t));
+            work_list = nullptr;
+            n_work = e->n;
+            acc = DevCounters{};
+            e->stats.workspace_retries++;
+            continue;
+        }
+        if (hc.n_overflow == 0) break;
+        if (attempt > 8) { set_err(e, "workspace keeps overflowing (need %llu bytes)", hc.slab_need_max); return WFL_ERR_CUDA; }
+        // replay the contigs that outgrew their workspace with a slab of the size they asked for
+        std::vector<uint8_t> st((size_t)e->n);
+        CU(cudaMemcpy(st.data(), e->o.status, (size_t)e->n, cudaMemcpyDeviceToHost));
+        replay.clear();
+        for (int64_t c = 0; c < e->n; ++c)
+            if (st[c] == 1) replay.push_back(c);
+        e->stats.workspace_retries += (int64_t)replay.size();
+        slab_bytes = std::max<size_t>((size_t)hc.slab_need_max, 2 * slab_bytes);
+        slab_bytes = (slab_bytes + 255) & ~size_t(255);
+        size_t budget = size_t(8) << 30;
+        grid = (int)std::max<size_t>(1, std::min<size_t>({(size_t)grid, replay.size(), budget / slab_bytes}));
+        int64_t *wl;
+        if ((rc = outbuf(e, e->work, replay.size(), &wl))) return rc;
+        CU(cudaMemcpyAsync(wl, replay.data(), replay.size() * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+        work_list = wl;
+        n_work = (int64_t)replay.size();
+    }
+    CompactArgs ca{};
+    ca.n = e->n;
+    ca.o = e->o;
+    ca.member_off = cm_off;
+    ca.n_members_a = cm_na;
+    ca.call_counts = cm_counts;
+    ca.call_index = cm_index;
+    ca.scan_tmp = scan_tmp;
+    ca.totals = cm_totals;
+    // members: compact into a buffer as large as the staging pool
+    int32_t *cm_members;
+    if ((rc = outbuf(e, e->cm[4], (size_t)e->o.mem_pool_cap, &cm_members))) return rc;
+    ca.members = cm_members;
+    ca.members_cap = e->o.mem_pool_cap;
+    e->stats.kernel_launches += launch_compaction(ca, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev[3], e->stream));
+    int64_t totals[4];
+    CU(cudaMemcpyAsync(totals, cm_totals, sizeof totals, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->members_total = totals[0];
+    e->stats.matched_pairs = (int64_t)acc.matched_pairs;
+    e->stats.groups = (int64_t)acc.groups;
+    e->stats.levels = (int64_t)acc.levels;
+    e->stats.pairs_tested = (int64_t)acc.pairs_tested;
+    e->stats.pairs_scored = (int64_t)acc.pairs_scored;
+    e->stats.smem_contigs = (int64_t)acc.smem_contigs;
+    CU(cudaEventElapsedTime(&e->stats.ms_score_kernel, e->ev[1], e->ev[2]));
+    CU(cudaEventElapsedTime(&e->stats.ms_kernels, e->ev[1], e->ev[3]));
+    e->have_results = true;
+    return WFL_OK;
+}
+
+int upload_batch(wfl_engine *e, const wfl_batch *in) {
+    if (!e->have_params || !e->have_tax) {
+        set_err(e, "set params and taxonomy before uploading a batch");
+        return WFL_ERR_STATE;
+    }
+    int rc = check_batch(e, in);
+    if (rc) return rc;
+    e->have_batch = e->have_results = false;
+    e->n = in->n_contigs;
+    e->nh = in->n_hits;
+    e->nl = in->n_loci;
+    e->S = e->P.p.n_systems;
+    DevBatch &b = e->b;
+    b.n_contigs = e->n;
+    b.n_hits = e->nh;
+    b.n_loci = e->nl;
+    const size_t n1 = (size_t)e->n + 1, nh = (size_t)e->nh, nl = (size_t)e->nl;
+    CU(cudaEventRecord(e->ev[0], e->stream));
+    if ((rc = upload(e, e->in[0], in->hit_off, n1, &b.hit_off))) return rc;
+    if ((rc = upload(e, e->in[1], in->locus_off, n1, &b.locus_off))) return rc;
+    if ((rc = upload(e, e->in[2], in->hit_qstart, nh, &b.hit_qstart))) return rc;
+    if ((rc = upload(e, e->in[3], in->hit_qend, nh, &b.hit_qend))) return rc;
+    if ((rc = upload(e, e->in[4], in->hit_taxon, nh, &b.hit_taxon))) return rc;
+    if ((rc = upload(e, e->in[5], in->hit_score, nh, &b.hit_score))) return rc;
+    if ((rc = upload(e, e->in[6], in->hit_scov, nh, &b.hit_scov))) return rc;
+    if ((rc = upload(e, e->in[7], in->hit_strand, nh, &b.hit_strand))) return rc;
+    b.hit_sysmask = nullptr;
+    if (e->S > 0 && (rc = upload(e, e->in[8], in->hit_sysmask, nh, &b.hit_sysmask))) return rc;
+    if ((rc = upload(e, e->in[9], in->locus_start, nl, &b.locus_start))) return rc;
+    if ((rc = upload(e, e->in[10], in->locus_end, nl, &b.locus_end))) return rc;
+    if ((rc = upload(e, e->in[11], in->locus_strand, nl, &b.locus_strand))) return rc;
+    CU(cudaEventRecord(e->ev[1], e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaEventElapsedTime(&e->stats.ms_h2d, e->ev[0], e->ev[1]));
+    e->have_batch = true;
+    return WFL_OK;
+}
+
+template <class T>
+int d2h(wfl_engine *e, T *dst, const T *src, size_t n) {
+    if (!dst || n == 0) return WFL_OK;
+    CU(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    return WFL_OK;
+}
+
+int download(wfl_engine *e, wfl_results *out) {
+    if (!e->have_results) {
+        set_err(e, "no results to download");
+        return WFL_ERR_STATE;
+    }
+    if (!out) { set_err(e, "null results"); return WFL_ERR_ARG; }
+    out->members_used = e->members_total;
+    if (out->members && out->members_capacity < e->members_total) {
+        set_err(e, "members buffer too small: need %lld", (long long)e->members_total);
+        return WFL_ERR_CAPACITY;
+    }
+    const size_t n = (size_t)e->n, nl = (size_t)e->nl, S = (size_t)e->S;
+    const DevOut &o = e->o;
+    int rc = 0;
+    float h2d = e->stats.ms_h2d;
+    CU(cudaEventRecord(e->ev[4], e->stream));
+    rc |= d2h(e, out->call, o.call, n);
+    rc |= d2h(e, out->direction, o.direction, n);
+    rc |= d2h(e, out->lifts, o.lifts, n);
+    rc |= d2h(e, out->clade1, o.clade1, n);
+    rc |= d2h(e, out->clade2, o.clade2, n);
+    rc |= d2h(e, out->lca, o.lca, n);
+    rc |= d2h(e, out->best1, o.best1, n);
+    rc |= d2h(e, out->best2, o.best2, n);
+    rc |= d2h(e, out->crit, o.crit, n);
+    rc |= d2h(e, out->rank, o.rank, n);
+    rc |= d2h(e, out->synteny, o.synteny, nl);
+    rc |= d2h(e, out->locus_flags, o.locus_flags, nl);
+    rc |= d2h(e, out->ann_winner, o.ann_winner, nl * S);
+    rc |= d2h(e, out->member_off, static_cast<const int64_t *>(e->cm[0].p), n + 1);
+    rc |= d2h(e, out->n_members_a, static_cast<const int32_t *>(e->cm[1].p), n);
+    rc |= d2h(e, out->members, static_cast<const int32_t *>(e->cm[4].p), (size_t)e->members_total);
+    rc |= d2h(e, out->call_counts, static_cast<const int64_t *>(e->cm[2].p), 3);
+    rc |= d2h(e, out->call_index, static_cast<const int64_t *>(e->cm[3].p), n);
+    if (rc) return WFL_ERR_CUDA;
+    CU(cudaEventRecord(e->ev[5], e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaEventElapsedTime(&e->stats.ms_d2h, e->ev[4], e->ev[5]));
+    e->stats.ms_h2d = h2d;
+    return WFL_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// exported entry points
+// ---------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int wfl_abi_version(void) { return WFL_ABI_VERSION; }
+
+int wfl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int wfl_create(int device, wfl_engine **out) {
+    if (!out) return WFL_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return WFL_ERR_CUDA;
+    wfl_engine *e = new wfl_engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return WFL_ERR_CUDA;
+    }
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    for (auto &ev : e->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) {
+            delete e;
+            return WFL_ERR_CUDA;
+        }
+    *out = e;
+    return WFL_OK;
+}
+
+void wfl_destroy(wfl_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    auto fr = [](Buf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
+    for (auto &b : e->tx) fr(b);
+    for (auto &b : e->in) fr(b);
+    for (auto &b : e->out) fr(b);
+    for (auto &b : e->cm) fr(b);
+    for (auto &b : e->dbg) fr(b);
+    fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch);
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char *wfl_last_error(const wfl_engine *e) { return e ? e->err.c_str() : "null engine"; }
+
+int wfl_set_params(wfl_engine *e, const wfl_params *p) {
+    if (!e || !p) return WFL_ERR_ARG;
+    if (p->n_systems < 0 || p->n_systems > WFL_MAX_SYSTEMS || p->disambiguate_one < 0 || p->disambiguate_one > 1 ||
+        p->disambiguate_two < 0 || p->disambiguate_two > 2 || p->weak_loci < 0 || p->weak_loci > 2 ||
+        p->ambiguous_threshold < 0 || p->ambiguous_threshold > 2 || p->sister_penalty < 0 ||
+        p->sister_penalty > 2 || p->annotation_threshold < 0 || p->annotation_threshold > 2 ||
+        p->jump_taxonomy < 0) {
+        set_err(e, "parameter out of range");
+        return WFL_ERR_ARG;
+    }
+    DevParams &P = e->P;
+    P.p = *p;
+    P.min_thr = std::min(p->k1, p->k2);   // waafle_orgscorer.py:338-339
+    P.max_thr = std::max(p->k1, p->k2);
+    const bool k1_is_min = p->k1 <= p->k2;
+    const int sel_min = k1_is_min ? 0 : 1, sel_max = k1_is_min ? 1 : 0;
+    const double tri[3] = {1e-6, P.min_thr, P.max_thr};   // off / lenient / strict
+    P.ann_thr = tri[p->annotation_threshold];             // :341-346
+    P.k_amb = tri[p->ambiguous_threshold];                // :515-516
+    P.amb_sel = p->ambiguous_threshold == 0 ? 2 : (p->ambiguous_threshold == 1 ? sel_min : sel_max);
+    P.sister_thr = p->sister_penalty == 1 ? P.max_thr : P.min_thr;   // :720-721
+    P.sis_sel = p->sister_penalty == 1 ? sel_max : sel_min;
+    e->have_params = true;
+    e->have_batch = e->have_results = false;
+    return WFL_OK;
+}
+
+int wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent, const int32_t *depth,
+                     const int32_t *leaf_count, const uint8_t *listed, int32_t root_idx, int32_t unknown_idx) {
+    if (!e) return WFL_ERR_ARG;
+    if (n_nodes <= 0 || !parent || !depth || !leaf_count || !listed || root_idx < 0 || root_idx >= n_nodes ||
+        unknown_idx < 0 || unknown_idx >= n_nodes) {
+        set_err(e, "bad taxonomy arguments");
+        return WFL_ERR_ARG;
+    }
+    if (parent[root_idx] != root_idx || depth[root_idx] != 0) {
+        set_err(e, "root must be its own parent at depth 0");
+        return WFL_ERR_ARG;
+    }
+    for (int32_t i = 0; i < n_nodes; ++i) {
+        int32_t p = parent[i];
+        if (p < 0 || p >= n_nodes || (i != root_idx && depth[i] != depth[p] + 1)) {
+            set_err(e, "taxonomy node %d: parent / depth inconsistent", i);
+            return WFL_ERR_ARG;
+        }
+    }
+    CU(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = upload(e, e->tx[0], parent, (size_t)n_nodes, &e->tax.parent))) return rc;
+    if ((rc = upload(e, e->tx[1], depth, (size_t)n_nodes, &e->tax.depth))) return rc;
+    if ((rc = upload(e, e->tx[2], leaf_count, (size_t)n_nodes, &e->tax.leaf_count))) return rc;
+    if ((rc = upload(e, e->tx[3], listed, (size_t)n_nodes, &e->tax.listed))) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    e->tax.n_nodes = n_nodes;
+    e->tax.root = root_idx;
+    e->tax.unknown = unknown_idx;
+    e->have_tax = true;
+    e->have_batch = e->have_results = false;
+    return WFL_OK;
+}
+
+int wfl_upload_batch(wfl_engine *e, const wfl_batch *in) {
+    if (!e) return WFL_ERR_ARG;
+    CU(cudaSetDevice(e->device));
+    return upload_batch(e, in);
+}
+
+int wfl_run_resident(wfl_engine *e) {
+    if (!e) return WFL_ERR_ARG;
+    CU(cudaSetDevice(e->device));
+    float h2d = e->stats.ms_h2d;
+    int rc = run_kernels(e);
+    e->stats.ms_h2d = h2d;
+    return rc;
+}
+
+int wfl_download_results(wfl_engine *e, wfl_results *out) {
+    if (!e) return WFL_ERR_ARG;
+    CU(cudaSetDevice(e->device));
+    return download(e, out);
+}
+
+int wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out) {
+    if (!e) return WFL_ERR_ARG;
+    CU(cudaSetDevice(e->device));
+    int rc = upload_batch(e, in);
+    if (rc) return rc;
+    float h2d = e->stats.ms_h2d;
+    if ((rc = run_kernels(e))) return rc;
+    e->stats.ms_h2d = h2d;
+    return download(e, out);
+}
+
+int wfl_get_stats(const wfl_engine *e, wfl_stats *out) {
+    if (!e || !out) return WFL_ERR_ARG;
+    *out = e->stats;
+    return WFL_OK;
+}
+
+int wfl_configure(wfl_engine *e, int threads, int smem_bytes, int ctas_per_sm) {
+    if (!e) return WFL_ERR_ARG;
+    if (threads) {
+        if (threads < 32 || threads > 1024 || threads % 32) { set_err(e, "threads must be a multiple of 32 in [32,1024]"); return WFL_ERR_ARG; }
+        e->threads = threads;
+    }
+    if (smem_bytes) {
+        if (smem_bytes < 0 || (size_t)smem_bytes + 2048 > e->smem_optin) { set_err(e, "smem_bytes too large"); return WFL_ERR_ARG; }
+        e->smem_bytes = smem_bytes & ~15;
+    }
+    if (ctas_per_sm) {
+        if (ctas_per_sm < 1 || ctas_per_sm > 32) { set_err(e, "ctas_per_sm out of range"); return WFL_ERR_ARG; }
+        e->ctas_per_sm = ctas_per_sm;
+    }
+    return WFL_OK;
+}
+
+int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int32_t *locus, double *score,
+                              int64_t capacity) {
+    if (!e) return WFL_ERR_ARG;
+    if (!e->have_batch) { set_err(e, "no resident batch"); return WFL_ERR_STATE; }
+    if (contig < 0 || contig >= e->n || capacity < 0) { set_err(e, "bad contig index"); return WFL_ERR_ARG; }
+    CU(cudaSetDevice(e->device));
+    int rc = alloc_outputs(e);
+    if (rc) return rc;
+    DevCounters *ctr;
+    int32_t *dc, *dl;
+    double *ds;
+    long long *dn;
+    int64_t *wl;
+    char *slab;
+    size_t cap = (size_t)std::max<int64_t>(capacity, 1);
+    if ((rc = outbuf(e, e->ctr, 1, &ctr)) || (rc = outbuf(e, e->dbg[0], cap, &dc)) ||
+        (rc = outbuf(e, e->dbg[1], cap, &dl)) || (rc = outbuf(e, e->dbg[2], cap, &ds)) ||
+        (rc = outbuf(e, e->dbg[3], 1, &dn)) || (rc = outbuf(e, e->work, 1, &wl)))
+        return rc;
+    size_t slab_bytes = size_t(256) << 20;   // one CTA, generous
+    if ((rc = outbuf(e, e->slab, slab_bytes, &slab))) return rc;
+    CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
+    CU(cudaMemsetAsync(dn, 0, sizeof(long long), e->stream));
+    CU(cudaMemcpyAsync(wl, &contig, sizeof contig, cudaMemcpyHostToDevice, e->stream));
+    ScoreArgs a{};
+    a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
+    a.work_list = wl; a.n_work = 1; a.slab = slab; a.slab_bytes = slab_bytes; a.smem_bytes = e->smem_bytes;
+    a.dbg_contig = contig; a.dbg_clade = dc; a.dbg_locus = dl; a.dbg_score = ds; a.dbg_cap = capacity; a.dbg_count = dn;
+    launch_score_kernel(a, 1, e->threads, e->stream);
+    CU(cudaGetLastError());
+    long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, dn, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    size_t m = (size_t)std::min<long long>(cnt, capacity);
+    if (m) {
+        CU(cudaMemcpy(clade, dc, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(locus, dl, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(score, ds, m * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    e->have_results = false;
+    return cnt;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Device-side data structures shared by the kernels and the C-ABI host code.
+// Hand-written for sm_100a; no library kernels on the path.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "waafle_b200.h"
+
+namespace wfl {
+
+// Read-only taxonomy tables (host flattening of waafle/utils.py:374-447).
+struct DevTax {
+    const int32_t *parent;
+    const int32_t *depth;
+    const int32_t *leaf_count;
+    const uint8_t *listed;
+    int32_t n_nodes, root, unknown;
+};
+
+// The resident batch (wfl_batch with device pointers).
+struct DevBatch {
+    int64_t n_contigs, n_hits, n_loci;
+    const int64_t *hit_off, *locus_off;
+    const int32_t *hit_qstart, *hit_qend, *hit_taxon;
+    const double *hit_score, *hit_scov;
+    const int8_t *hit_strand;
+    const uint32_t *hit_sysmask;
+    const int32_t *locus_start, *locus_end;
+    const int8_t *locus_strand;
+};
+
+// Result arrays on the device (wfl_results) plus the member staging pool.
+struct DevOut {
+    uint8_t *call, *direction;
+    int32_t *lifts, *clade1, *clade2, *lca, *best1, *best2;
+    double *crit, *rank;
+    uint8_t *synteny, *locus_flags;
+    int32_t *ann_winner;
+    // members are bump-allocated in a staging pool by the scoring kernel, then compacted
+    // into contig order (CSR) by the compaction kernels
+    int32_t *n_mem_a, *n_mem_b;
+    int64_t *mem_pos;
+    int32_t *mem_pool;
+    int64_t mem_pool_cap;
+    uint8_t *status;          // per contig: 0 ok, 1 workspace overflow (replay), 2 runaway
+};
+
+// Global counters (one struct in device memory, zeroed before each run).
+struct DevCounters {
+    unsigned long long next_work;       // work-queue head
+    unsigned long long mem_pool_used;   // staging pool bump pointer (may exceed capacity)
+    unsigned long long slab_need_max;   // max workspace bytes any contig asked for
+    unsigned long long n_overflow;      // contigs that overflowed their workspace
+    unsigned long long n_runaway;
+    unsigned long long matched_pairs, groups, levels, pairs_tested, pairs_scored, smem_contigs;
+};
+
+// Thresholds derived once on the host (waafle_orgscorer.py:338-346, 515-516, 720-721).
+struct DevParams {
+    wfl_params p;
+    double min_thr, max_thr, ann_thr, k_amb, sister_thr;
+    int amb_sel, sis_sel;     // which of the three per-clade masks (0:k1 1:k2 2:eps) to use
+};
+
+struct ScoreArgs {
+    DevBatch b;
+    DevTax t;
+    DevOut o;
+    DevParams P;
+    DevCounters *ctr;
+    const int64_t *work_list;   // optional list of contig indices (replays); null = 0..n-1
+    int64_t n_work;
+    char *slab;                 // per-CTA global workspace, slab_bytes each
+    size_t slab_bytes;
+    int smem_bytes;             // dynamic shared memory per CTA
+    // test hook: dump the level-0 gene scores of one contig as COO triples
+    long long dbg_contig;       // -1 = off
+    int32_t *dbg_clade, *dbg_locus;
+    double *dbg_score;
+    long long dbg_cap;
+    long long *dbg_count;
+};
+
+void launch_score_kernel(const ScoreArgs &a, int grid, int threads, cudaStream_t s);
+
+// Compaction (K10): CSR of melded members in contig order + contig indices grouped by call.
+struct CompactArgs {
+    int64_t n;
+    DevOut o;
+    int64_t *member_off;      // [n+1]
+    int32_t *n_members_a;     // [n]
+    int32_t *members;         // compacted
+    int64_t members_cap;
+    int64_t *call_counts;     // [3]
+    int64_t *call_index;      // [n]
+    int64_t *scan_tmp;        // [4 * n_blocks] scratch
+    int64_t *totals;          // [4]: members, lgt, no_lgt, unclassified
+};
+int launch_compaction(const CompactArgs &a, cudaStream_t s);   // returns kernels launched
+size_t compaction_scratch_elems(int64_t n);
+
+}  // namespace wfl

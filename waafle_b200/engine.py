@@ -1,0 +1,260 @@
+"""ctypes binding of the C ABI (include/waafle_b200.h) and the `Engine` host object.
+
+`Engine.score_batch` is the call that replaces the body of the reference's major contig
+loop (waafle/waafle_orgscorer.py:952-960).  There is no CPU fallback: if the CUDA library
+is missing or no GPU is visible, construction fails loudly.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+from .params import CParams, OrgscorerParams
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libwaafle_b200.so")
+
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_i8p = ctypes.POINTER(ctypes.c_int8)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+EXPORTS = ["wfl_abi_version", "wfl_device_count", "wfl_create", "wfl_destroy", "wfl_last_error",
+           "wfl_set_params", "wfl_set_taxonomy", "wfl_score_batch", "wfl_upload_batch",
+           "wfl_run_resident", "wfl_download_results", "wfl_get_stats", "wfl_configure",
+           "wfl_debug_gene_scores"]
+
+
+class CBatch(ctypes.Structure):
+    """`wfl_batch`."""
+    _fields_ = [("n_contigs", ctypes.c_int64), ("n_hits", ctypes.c_int64), ("n_loci", ctypes.c_int64),
+                ("hit_off", c_i64p), ("locus_off", c_i64p),
+                ("hit_qstart", c_i32p), ("hit_qend", c_i32p), ("hit_taxon", c_i32p),
+                ("hit_score", c_f64p), ("hit_scov", c_f64p), ("hit_strand", c_i8p),
+                ("hit_sysmask", c_u32p),
+                ("locus_start", c_i32p), ("locus_end", c_i32p), ("locus_strand", c_i8p)]
+
+
+class CResults(ctypes.Structure):
+    """`wfl_results`."""
+    _fields_ = [("call", c_u8p), ("direction", c_u8p), ("lifts", c_i32p), ("clade1", c_i32p),
+                ("clade2", c_i32p), ("lca", c_i32p), ("best1", c_i32p), ("best2", c_i32p),
+                ("crit", c_f64p), ("rank", c_f64p), ("member_off", c_i64p),
+                ("n_members_a", c_i32p), ("members", c_i32p),
+                ("members_capacity", ctypes.c_int64), ("members_used", ctypes.c_int64),
+                ("synteny", c_u8p), ("locus_flags", c_u8p), ("ann_winner", c_i32p),
+                ("call_counts", c_i64p), ("call_index", c_i64p)]
+
+
+class CStats(ctypes.Structure):
+    """`wfl_stats`."""
+    _fields_ = [(k, ctypes.c_int64) for k in
+                ("kernel_launches", "contigs", "hits", "loci", "matched_pairs", "groups", "levels",
+                 "pairs_tested", "pairs_scored", "workspace_retries", "smem_contigs")] + \
+               [(k, ctypes.c_float) for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_score_kernel")]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the engine; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError("CUDA engine library not built: {} (run `python -m waafle_b200.build`)"
+                          .format(path))
+    lib = ctypes.CDLL(path)
+    lib.wfl_abi_version.restype = ctypes.c_int
+    lib.wfl_device_count.restype = ctypes.c_int
+    lib.wfl_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.wfl_destroy.argtypes = [ctypes.c_void_p]
+    lib.wfl_destroy.restype = None
+    lib.wfl_last_error.argtypes = [ctypes.c_void_p]
+    lib.wfl_last_error.restype = ctypes.c_char_p
+    lib.wfl_set_params.argtypes = [ctypes.c_void_p, ctypes.POINTER(CParams)]
+    lib.wfl_set_taxonomy.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_i32p, c_i32p, c_u8p,
+                                     ctypes.c_int32, ctypes.c_int32]
+    lib.wfl_score_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(CBatch), ctypes.POINTER(CResults)]
+    lib.wfl_upload_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(CBatch)]
+    lib.wfl_run_resident.argtypes = [ctypes.c_void_p]
+    lib.wfl_download_results.argtypes = [ctypes.c_void_p, ctypes.POINTER(CResults)]
+    lib.wfl_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(CStats)]
+    lib.wfl_configure.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.wfl_debug_gene_scores.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_i32p, c_i32p, c_f64p,
+                                          ctypes.c_int64]
+    lib.wfl_debug_gene_scores.restype = ctypes.c_int64
+    if path == _LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def _as(a, dtype):
+    a = np.asarray(a)
+    if a.dtype != dtype or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Engine:
+    """One handle on one GPU."""
+
+    def __init__(self, device=0, params=None, taxonomy=None):
+        self._lib = load_library()
+        if self._lib.wfl_abi_version() != 1:
+            raise EngineError("ABI version mismatch")
+        h = ctypes.c_void_p()
+        rc = self._lib.wfl_create(int(device), ctypes.byref(h))
+        if rc != 0 or not h:
+            raise EngineError("wfl_create(device={}) failed with {}: no usable CUDA device "
+                              "(this engine has no CPU fallback)".format(device, rc))
+        self._h = h
+        self.device = device
+        self._keep = {}
+        self.n_systems = 0
+        if params is not None:
+            self.set_params(params)
+        if taxonomy is not None:
+            self.set_taxonomy(taxonomy)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.wfl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError("waafle_b200 engine error {}: {}".format(
+                rc, self._lib.wfl_last_error(self._h).decode()))
+
+    # ------------------------------------------------------------------
+    def configure(self, threads=0, smem_bytes=0, ctas_per_sm=0):
+        self._check(self._lib.wfl_configure(self._h, threads, smem_bytes, ctas_per_sm))
+
+    def set_params(self, params):
+        if isinstance(params, dict):
+            params = OrgscorerParams(**params)
+        self.n_systems = params.n_systems
+        cp = params.as_ctypes()
+        self._check(self._lib.wfl_set_params(self._h, ctypes.byref(cp)))
+
+    def set_taxonomy(self, tax):
+        """`tax`: taxonomy.Taxonomy (built) or the dict of its tables()."""
+        t = tax.tables() if hasattr(tax, "tables") else tax
+        parent, depth = _as(t["parent"], np.int32), _as(t["depth"], np.int32)
+        leaf, listed = _as(t["leaf_count"], np.int32), _as(t["listed"], np.uint8)
+        self._check(self._lib.wfl_set_taxonomy(
+            self._h, len(parent), _ptr(parent, ctypes.c_int32), _ptr(depth, ctypes.c_int32),
+            _ptr(leaf, ctypes.c_int32), _ptr(listed, ctypes.c_uint8),
+            int(t["root_idx"]), int(t["unknown_idx"])))
+
+    # ------------------------------------------------------------------
+    def _cbatch(self, batch):
+        a = batch.arrays() if hasattr(batch, "arrays") else batch
+        k = dict(
+            hit_off=_as(a["hit_off"], np.int64), locus_off=_as(a["locus_off"], np.int64),
+            hit_qstart=_as(a["hit_qstart"], np.int32), hit_qend=_as(a["hit_qend"], np.int32),
+            hit_taxon=_as(a["hit_taxon"], np.int32), hit_score=_as(a["hit_score"], np.float64),
+            hit_scov=_as(a["hit_scov"], np.float64), hit_strand=_as(a["hit_strand"], np.int8),
+            locus_start=_as(a["locus_start"], np.int32), locus_end=_as(a["locus_end"], np.int32),
+            locus_strand=_as(a["locus_strand"], np.int8))
+        n, nh, nl = len(k["hit_off"]) - 1, len(k["hit_qstart"]), len(k["locus_start"])
+        cb = CBatch(n_contigs=n, n_hits=nh, n_loci=nl)
+        for name, arr in k.items():
+            setattr(cb, name, _ptr(arr, dict(CBatch._fields_)[name]._type_))
+        if self.n_systems > 0:
+            if a.get("hit_sysmask") is None:
+                raise EngineError("params.n_systems > 0 but the batch has no hit_sysmask")
+            k["hit_sysmask"] = _as(a["hit_sysmask"], np.uint32)
+            cb.hit_sysmask = _ptr(k["hit_sysmask"], ctypes.c_uint32)
+        self._keep = k   # keep the arrays alive while the C side reads them
+        return cb, n, nh, nl
+
+    def _alloc_results(self, n, nl, members_capacity):
+        S = self.n_systems
+        r = dict(
+            call=np.empty(n, np.uint8), direction=np.empty(n, np.uint8),
+            lifts=np.empty(n, np.int32), clade1=np.empty(n, np.int32),
+            clade2=np.empty(n, np.int32), lca=np.empty(n, np.int32), best1=np.empty(n, np.int32),
+            best2=np.empty(n, np.int32), crit=np.empty(n, np.float64), rank=np.empty(n, np.float64),
+            member_off=np.empty(n + 1, np.int64), n_members_a=np.empty(n, np.int32),
+            members=np.empty(max(1, members_capacity), np.int32),
+            synteny=np.empty(nl, np.uint8), locus_flags=np.empty(nl, np.uint8),
+            ann_winner=np.empty((nl, S), np.int32),
+            call_counts=np.empty(3, np.int64), call_index=np.empty(n, np.int64))
+        cr = CResults(members_capacity=len(r["members"]), members_used=0)
+        for name, arr in r.items():
+            setattr(cr, name, _ptr(arr, dict(CResults._fields_)[name]._type_))
+        return r, cr
+
+    def _finish(self, r, cr):
+        r["members"] = r["members"][:cr.members_used]
+        return r
+
+    def score_batch(self, batch):
+        """Host arrays in, host arrays out (H2D + kernels + D2H inside the call)."""
+        cb, n, nh, nl = self._cbatch(batch)
+        cap = max(4 * n, 1024)
+        for _ in range(2):
+            r, cr = self._alloc_results(n, nl, cap)
+            rc = self._lib.wfl_score_batch(self._h, ctypes.byref(cb), ctypes.byref(cr))
+            if rc == -4:   # WFL_ERR_CAPACITY: results are resident, fetch with a larger buffer
+                cap = int(cr.members_used)
+                r, cr = self._alloc_results(n, nl, cap)
+                rc = self._lib.wfl_download_results(self._h, ctypes.byref(cr))
+            self._check(rc)
+            return self._finish(r, cr)
+
+    def upload(self, batch):
+        cb, n, nh, nl = self._cbatch(batch)
+        self._check(self._lib.wfl_upload_batch(self._h, ctypes.byref(cb)))
+        self._resident = (n, nl)
+
+    def run_resident(self):
+        self._check(self._lib.wfl_run_resident(self._h))
+
+    def download(self):
+        n, nl = self._resident
+        r, cr = self._alloc_results(n, nl, max(4 * n, 1024))
+        rc = self._lib.wfl_download_results(self._h, ctypes.byref(cr))
+        if rc == -4:
+            r, cr = self._alloc_results(n, nl, int(cr.members_used))
+            rc = self._lib.wfl_download_results(self._h, ctypes.byref(cr))
+        self._check(rc)
+        return self._finish(r, cr)
+
+    def stats(self):
+        s = CStats()
+        self._check(self._lib.wfl_get_stats(self._h, ctypes.byref(s)))
+        return {k: getattr(s, k) for k, _ in CStats._fields_}
+
+    def debug_gene_scores(self, contig, capacity=1 << 16):
+        """Level-0 gene scores of one contig of the resident batch: (clade, locus, score)."""
+        cl, lo, sc = (np.empty(capacity, np.int32), np.empty(capacity, np.int32),
+                      np.empty(capacity, np.float64))
+        m = self._lib.wfl_debug_gene_scores(self._h, int(contig), _ptr(cl, ctypes.c_int32),
+                                            _ptr(lo, ctypes.c_int32), _ptr(sc, ctypes.c_double),
+                                            capacity)
+        if m < 0:
+            self._check(int(m))
+        if m > capacity:
+            return self.debug_gene_scores(contig, int(m))
+        return cl[:m], lo[:m], sc[:m]
