@@ -132,6 +132,9 @@ typedef struct {
     int64_t pairs_scored;       /* two-clade pairs that passed the mask test             */
     int64_t workspace_retries;  /* contigs replayed with a larger workspace              */
     int64_t smem_contigs;       /* contigs whose whole working set stayed in shared mem  */
+    int64_t phase_cycles[12];   /* per-phase SM cycles summed over contigs (profiling aid):
+                                   0 loci+count 1 fill+annot 2 sort 3 group 4 envelope 5 weak/masks
+                                   6 one-clade 7 two-clade 8 output */
     float   ms_h2d, ms_kernels, ms_d2h, ms_score_kernel;   /* CUDA-event times         */
 } wfl_stats;
 

@@ -218,6 +218,7 @@ int run_kernels(wfl_engine *e) {
         acc.pairs_tested += hc.pairs_tested;
         acc.pairs_scored += hc.pairs_scored;
         acc.smem_contigs += hc.smem_contigs;
+        for (int q = 0; q < 12; ++q) acc.phase_cycles[q] += hc.phase_cycles[q];
         if (hc.n_runaway) {
             set_err(e, "Runaway taxonomic recursion in %llu contig(s)", hc.n_runaway);
             return WFL_ERR_RUNAWAY;
@@ -283,6 +284,7 @@ int run_kernels(wfl_engine *e) {
     e->stats.pairs_tested = (int64_t)acc.pairs_tested;
     e->stats.pairs_scored = (int64_t)acc.pairs_scored;
     e->stats.smem_contigs = (int64_t)acc.smem_contigs;
+    for (int q = 0; q < 12; ++q) e->stats.phase_cycles[q] = (int64_t)acc.phase_cycles[q];
     CU(cudaEventElapsedTime(&e->stats.ms_score_kernel, e->ev[1], e->ev[2]));
     CU(cudaEventElapsedTime(&e->stats.ms_kernels, e->ev[1], e->ev[3]));
     e->have_results = true;

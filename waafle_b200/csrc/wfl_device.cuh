@@ -54,6 +54,7 @@ struct DevCounters {
     unsigned long long n_overflow;      // contigs that overflowed their workspace
     unsigned long long n_runaway;
     unsigned long long matched_pairs, groups, levels, pairs_tested, pairs_scored, smem_contigs;
+    unsigned long long phase_cycles[12];   // thread-0 clock64 deltas per phase (profiling aid)
 };
 
 // Thresholds derived once on the host (waafle_orgscorer.py:338-346, 515-516, 720-721).

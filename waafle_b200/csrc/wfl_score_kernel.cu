@@ -33,7 +33,7 @@ namespace {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-constexpr int KEY_LOCUS_BITS = 20;                 // retained loci per contig < 2^20
+constexpr int KEY_LOCUS_BITS = 32;                 // group key = clade << 32 | locus
 constexpr u64 KEY_LOCUS_MASK = (1ull << KEY_LOCUS_BITS) - 1;
 constexpr int MAX_WARPS = 32;
 
@@ -276,6 +276,9 @@ struct SiteSrc {
     const double *rv;
     int rs, re, n, pos, run_end;
     double run_v;
+    // Records of a group arrive in DESCENDING score order, so the first record that covers
+    // `pos` is the envelope value there; the run ends where that record ends or where a
+    // higher-scoring record (all seen before it) starts.
     __device__ __forceinline__ void advance() {
         double v = 0.0;   // np.zeros(len(locus)), waafle_orgscorer.py:381
         int nx = n;
@@ -283,11 +286,11 @@ struct SiteSrc {
             u32 i = sidx[r];
             int a = ra[i], b = rb[i];
             if (a <= pos && pos < b) {
-                v = fmax(v, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
+                v = fmax(0.0, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
                 nx = min(nx, b);
-            } else if (a > pos) {
-                nx = min(nx, a);
+                break;
             }
+            if (a > pos) nx = min(nx, a);
         }
         run_v = v;
         run_end = nx;
@@ -499,6 +502,9 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
         Arena ar{smem_dyn, a.slab + (size_t)blockIdx.x * a.slab_bytes, (size_t)a.smem_bytes,
                  a.slab_bytes, 0, 0, true, true};
 
+        long long ph_last = clock64();
+        unsigned long long ph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PH(i) do { if (tid == 0) { long long t_ = clock64(); ph[i] += (unsigned long long)(t_ - ph_last); ph_last = t_; } } while (0)
         // ---- loci: --min-gene-length filter, GFF order kept (waafle_orgscorer.py:348-352) ----
         int *l_lo = ar.get<int>(Graw), *l_len = ar.get<int>(Graw), *l_raw = ar.get<int>(Graw);
         signed char *l_str = ar.get<signed char>(Graw);
@@ -533,7 +539,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
         long long r_mem = 0;
         double r_crit = 0.0, r_rank = 0.0;
 
-        if (!overflow && H > 0 && G > 0 && G <= (int)KEY_LOCUS_MASK) {
+        if (!overflow && H > 0 && G > 0) {
             __syncthreads();
             // ---- K1 pass 1: count (hit, locus) matches -------------------------------------
             int cnt = 0;
@@ -553,6 +559,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                 }
             }
             const int M = block_sum(cnt, sh);
+            PH(0);
             int Mp2 = 1;
             while (Mp2 < M) Mp2 <<= 1;
             // worst case for this contig (groups <= M + G, clades <= groups): one replay suffices
@@ -565,7 +572,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
             u64 *key = ar.get<u64>(Mp2);
             u32 *sidx = ar.get<u32>(Mp2);
             int *r_a = ar.get<int>(M), *r_b = ar.get<int>(M), *r_cl = ar.get<int>(M),
-                *r_loc = ar.get<int>(M), *r_hit = S > 0 ? ar.get<int>(M) : nullptr;
+                *r_loc = ar.get<int>(M), *r_ord = ar.get<int>(M), *r_hit = S > 0 ? ar.get<int>(M) : nullptr;
             double *maxv = ar.get<double>(G);
             u64 *maxb = ar.get<u64>(G);
             unsigned char *ign = ar.get<unsigned char>(G + 1);
@@ -647,6 +654,26 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                     }
                 }
 
+                PH(1);
+                // ---- level-invariant base order: (locus, score descending) -----------------
+                // rank2[r] = position of record r in that order; every level then sorts by
+                // (clade, rank2), which groups by (clade, locus) with descending scores inside.
+                for (int r = tid; r < Mp2; r += B) {
+                    key[r] = r < M ? ~dbits(r_v[r]) : ~0ull;
+                    sidx[r] = (u32)r;
+                }
+                __syncthreads();
+                bitonic_sort(key, sidx, Mp2);
+                for (int r = tid; r < M; r += B) r_ord[sidx[r]] = r;
+                __syncthreads();
+                for (int r = tid; r < Mp2; r += B) {
+                    key[r] = r < M ? (((u64)(u32)r_loc[r] << 32) | (u64)(u32)r_ord[r]) : ~0ull;
+                    sidx[r] = (u32)r;
+                }
+                __syncthreads();
+                bitonic_sort(key, sidx, Mp2);
+                for (int r = tid; r < M; r += B) r_ord[sidx[r]] = r;
+                __syncthreads();
                 // ---- K9: level loop (evaluate_contig, waafle_orgscorer.py:566-583) ----------
                 const size_t mark_smem = ar.smem_used, mark_slab = ar.slab_used;
                 int n_levels = 0;
@@ -657,11 +684,16 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                     ++n_levels;
                     // ---- regroup: sort records by (clade, locus) ---------------------------
                     for (int r = tid; r < Mp2; r += B) {
-                        key[r] = r < M ? (((u64)(u32)r_cl[r] << KEY_LOCUS_BITS) | (u64)r_loc[r]) : ~0ull;
+                        key[r] = r < M ? (((u64)(u32)r_cl[r] << 32) | (u64)(u32)r_ord[r]) : ~0ull;
                         sidx[r] = (u32)r;
                     }
                     __syncthreads();
                     bitonic_sort(key, sidx, Mp2);
+                    // the rank has done its job: turn the sort key into the group key (clade, locus)
+                    for (int r = tid; r < M; r += B)
+                        key[r] = (key[r] & ~KEY_LOCUS_MASK) | (u64)(u32)r_loc[sidx[r]];
+                    __syncthreads();
+                    PH(2);
                     const u64 unk_lo = (u64)(u32)tax.unknown << KEY_LOCUS_BITS;
                     int ng = 0, nlt = 0, nu = 0;
                     for (int r = tid; r < M; r += B) {
@@ -711,6 +743,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                         }
                     for (int i = tid; i < G; i += B) maxb[i] = dbits(0.0);
                     __syncthreads();
+                    PH(3);
                     // ---- K2: envelope integral per group, numpy-pairwise-exact -------------
                     for (int g = tid; g < Ngrp; g += B) {
                         int rs = g_rs[g];
@@ -726,6 +759,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                             atomicMax(&maxb[loc], dbits(sc));
                     }
                     __syncthreads();
+                    PH(4);
                     // ---- K4: weak loci (waafle_orgscorer.py:412-427) -------------------------
                     for (int i = tid; i < G; i += B) {
                         double mx = dbits_inv(maxb[i]);
@@ -811,6 +845,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                     Level L{G, W, T, Ngrp, nun, g_loc, g_clade, g_score, cl_id, cl_go,
                             {mk0, mk1, mk2}, um, ign, l_len};
 
+                    PH(5);
                     // ---- K6: one-clade search (explain_one, waafle_orgscorer.py:585-597) ------
                     if (tid == 0) { sh.best_bits = 0; sh.best_idx = -1; }
                     __syncthreads();
@@ -832,6 +867,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                         if (cl_opt[t] && dbits(cl_rank[t]) == sh.best_bits)
                             atomicMax(&sh.best_idx, (long long)t);   // ties: last in name order
                     __syncthreads();
+                    PH(6);
                     if (sh.best_idx >= 0) {
                         // meld_one (waafle_orgscorer.py:621-631)
                         const int tb = (int)sh.best_idx;
@@ -983,6 +1019,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                             }
                         }
                     }
+                    PH(7);
                     if (r_call != WFL_CALL_UNCLASSIFIED) {
                         // ---- melded members -> staging pool (tails, waafle_orgscorer.py:630,658-659)
                         if (r_na + r_nb > 0) {
@@ -1014,7 +1051,9 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                     ++lifts;
                     __syncthreads();
                 }
+                PH(8);
                 if (tid == 0) {
+                    for (int q = 0; q < 9; ++q) atomicAdd(&a.ctr->phase_cycles[q], ph[q]);
                     atomicAdd(&a.ctr->matched_pairs, (unsigned long long)M);
                     atomicAdd(&a.ctr->groups, (unsigned long long)n_groups);
                     atomicAdd(&a.ctr->levels, (unsigned long long)n_levels);
@@ -1023,8 +1062,6 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                     if (ar.all_smem) atomicAdd(&a.ctr->smem_contigs, 1ull);
                 }
             }
-        } else if (!overflow && G > (int)KEY_LOCUS_MASK) {
-            overflow = true;
         }
 
         if (overflow) {

@@ -12,7 +12,7 @@ import numpy as np
 
 from .params import CParams, OrgscorerParams
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libwaafle_b200.so")
+_LIB_PATH = os.environ.get("WFL_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libwaafle_b200.so")
 
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -53,6 +53,7 @@ class CStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int64) for k in
                 ("kernel_launches", "contigs", "hits", "loci", "matched_pairs", "groups", "levels",
                  "pairs_tested", "pairs_scored", "workspace_retries", "smem_contigs")] + \
+               [("phase_cycles", ctypes.c_int64 * 12)] + \
                [(k, ctypes.c_float) for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_score_kernel")]
 
 
@@ -244,7 +245,9 @@ class Engine:
     def stats(self):
         s = CStats()
         self._check(self._lib.wfl_get_stats(self._h, ctypes.byref(s)))
-        return {k: getattr(s, k) for k, _ in CStats._fields_}
+        d = {k: getattr(s, k) for k, _ in CStats._fields_}
+        d["phase_cycles"] = list(d["phase_cycles"])
+        return d
 
     def debug_gene_scores(self, contig, capacity=1 << 16):
         """Level-0 gene scores of one contig of the resident batch: (clade, locus, score)."""

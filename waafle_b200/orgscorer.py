@@ -1,0 +1,127 @@
+"""`waafle_orgscorer` front end over the B200 engine.
+
+Same positional arguments and flags as the reference CLI (waafle/waafle_orgscorer.py:135-303 plus
+the shared flags of waafle/waafle_genecaller.py:81-101), same stderr stage messages, same three
+output TSVs.  The only part that differs is the body of the major contig loop
+(waafle_orgscorer.py:952-960), which is one `Engine.score_batch` call on the GPU.
+`--write-details` is accepted but rejected at run time (it crashes on Python 3 upstream).
+"""
+
+import argparse
+import os
+import sys
+
+from . import packing, parsers, taxonomy, writer
+from .engine import Engine
+from .params import OrgscorerParams
+from .utils import die, read_contig_lengths, say
+
+
+def get_args(argv=None):
+    parser = argparse.ArgumentParser(
+        description="Step 2 in the WAAFLE pipeline: merge blast hits into genes on contigs and "
+                    "identify contigs best explained by one clade vs. a pair of clades (putative LGT). "
+                    "B200-native engine.",
+        formatter_class=argparse.RawTextHelpFormatter)
+    g = parser.add_argument_group("required inputs")
+    g.add_argument("contigs", help="contigs file (.fasta format)")
+    g.add_argument("blastout", help="output of waafle_search for one set of contigs (.blastout)")
+    g.add_argument("gff", help="gene calls (from waafle_genecaller or user-supplied) for <contigs> (.gff)")
+    g.add_argument("taxonomy", help="taxonomy file for the blast database used to make <blastout>")
+    g = parser.add_argument_group("output formatting")
+    g.add_argument("--outdir", default=".", metavar="<path>")
+    g.add_argument("--basename", default=None, metavar="<str>")
+    g.add_argument("--write-details", action="store_true")
+    g.add_argument("--quiet", action="store_true")
+    g = parser.add_argument_group("main parameters")
+    g.add_argument("-k1", "--one-clade-threshold", type=float, default=0.5, metavar="<0.0-1.0>")
+    g.add_argument("-k2", "--two-clade-threshold", type=float, default=0.8, metavar="<0.0-1.0>")
+    g.add_argument("--disambiguate-one", choices=["report-best", "meld"], default="meld")
+    g.add_argument("--disambiguate-two", choices=["report-best", "jump", "meld"], default="meld")
+    g.add_argument("--range", type=float, default=0.05, metavar="<float>")
+    g.add_argument("--jump-taxonomy", type=int, default=None, metavar="<1-N>")
+    g = parser.add_argument_group("post-detection LGT filters")
+    g.add_argument("--allow-lca", action="store_true")
+    g.add_argument("--ambiguous-fraction", type=float, default=0.1, metavar="<0.0-1.0>")
+    g.add_argument("--ambiguous-threshold", choices=["off", "lenient", "strict"], default="lenient")
+    g.add_argument("--sister-penalty", choices=["off", "lenient", "strict"], default="strict")
+    g.add_argument("--clade-genes", type=int, default=None, metavar="<1-N>")
+    g.add_argument("--clade-leaves", type=int, default=None, metavar="<1-N>")
+    g = parser.add_argument_group("gene-hit merge parameters")
+    g.add_argument("--weak-loci", choices=["ignore", "penalize", "assign-unknown"], default="ignore")
+    g.add_argument("--annotation-threshold", choices=["off", "lenient", "strict"], default="lenient")
+    g.add_argument("--min-overlap", type=float, default=0.1, metavar="<0.0-1.0>")
+    g.add_argument("--min-gene-length", default=200, type=float, metavar="<int>")
+    g.add_argument("--min-scov", default=0.75, type=float, metavar="<float>")
+    g.add_argument("--stranded", action="store_true")
+    g = parser.add_argument_group("engine")
+    g.add_argument("--device", type=int, default=0, help="CUDA device index [default: 0]")
+    g.add_argument("--chunk-contigs", type=int, default=250000,
+                   help="contigs per engine call (streaming; results are merged) [default: 250000]")
+    return parser.parse_args(argv)
+
+
+def score_in_chunks(engine, batch, chunk):
+    """Contigs are independent, so a long run is scored chunk by chunk and concatenated."""
+    import numpy as np
+    if batch.n_contigs <= chunk:
+        return engine.score_batch(batch)
+    parts, c0 = [], 0
+    while c0 < batch.n_contigs:
+        c1 = min(batch.n_contigs, c0 + chunk)
+        r = engine.score_batch(batch.slice(c0, c1))
+        r["ann_winner"] = np.where(r["ann_winner"] >= 0, r["ann_winner"] + int(batch.hit_off[c0]), -1)
+        parts.append(r)
+        c0 = c1
+    out = {}
+    for k in parts[0]:
+        if k == "member_off":
+            offs, base = [np.zeros(1, np.int64)], 0
+            for p in parts:
+                offs.append(p[k][1:] + base)
+                base += int(p[k][-1])
+            out[k] = np.concatenate(offs)
+        elif k == "call_counts":
+            out[k] = sum(p[k] for p in parts)
+        elif k == "call_index":
+            continue
+        else:
+            out[k] = np.concatenate([p[k] for p in parts])
+    order = [np.nonzero(out["call"] == c)[0] for c in (2, 1, 0)]
+    out["call_index"] = np.concatenate(order).astype(np.int64)
+    return out
+
+
+def main(argv=None):
+    args = get_args(argv)
+    if args.write_details:
+        die("--write-details is not supported (it fails on Python 3 in the reference as well)")
+    say("Loading taxonomy.")
+    tax = taxonomy.Taxonomy(args.taxonomy)
+    say("Initializing contigs.")
+    contig_lengths = read_contig_lengths(args.contigs)
+    say("Adding gene coordinates.")
+    loci = parsers.read_gff_loci(args.gff)
+    if args.basename is None:
+        args.basename = os.path.split(args.contigs)[1].split(".")[0]
+    say("Analyzing contigs.")
+    hits = parsers.read_blast_hits(args.blastout)
+    if hits.sysmask is None:
+        die("more than 32 annotation systems in the subject headers")
+    tax.build(set(hits.taxon))
+    batch = packing.pack(contig_lengths, loci, hits, tax)
+    params = OrgscorerParams.from_args(args, n_systems=len(hits.systems))
+    engine = Engine(args.device, params, tax)
+    res = score_in_chunks(engine, batch, args.chunk_contigs)
+    if not args.quiet:
+        st = engine.stats()
+        say("  scored {:,} contigs / {:,} hits on cuda:{} ({:.1f} ms in kernels)".format(
+            batch.n_contigs, batch.n_hits, args.device, st["ms_kernels"]))
+    engine.close()
+    records = writer.build_records(batch, loci, hits, tax, res)
+    writer.write_main_output_files(records, args.outdir, args.basename)
+    say("Finished successfully.")
+
+
+if __name__ == "__main__":
+    main()
