@@ -35,7 +35,7 @@ struct wfl_engine {
     int64_t n = 0, nh = 0, nl = 0;
     int S = 0;
     // knobs
-    int threads = 128, smem_bytes = 36 * 1024, ctas_per_sm = 6;
+    int threads = 32, smem_bytes = 14 * 1024, ctas_per_sm = 12;
     size_t slab_bytes = 128 * 1024;
     // device buffers (grow-only)
     Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4];
@@ -205,7 +205,10 @@ int run_kernels(wfl_engine *e) {
         a.smem_bytes = e->smem_bytes;
         a.dbg_contig = -1;
         if (n_work > 0) {
-            launch_score_kernel(a, (int)std::min<int64_t>(grid, n_work), e->threads, e->stream);
+            if (e->threads == 32)
+                launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, n_work), e->stream);
+            else
+                launch_score_kernel(a, (int)std::min<int64_t>(grid, n_work), e->threads, e->stream);
             CU(cudaGetLastError());
             e->stats.kernel_launches++;
         }
@@ -579,7 +582,10 @@ int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int
     a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
     a.work_list = wl; a.n_work = 1; a.slab = slab; a.slab_bytes = slab_bytes; a.smem_bytes = e->smem_bytes;
     a.dbg_contig = contig; a.dbg_clade = dc; a.dbg_locus = dl; a.dbg_score = ds; a.dbg_cap = capacity; a.dbg_count = dn;
-    launch_score_kernel(a, 1, e->threads, e->stream);
+    if (e->threads == 32)
+        launch_score_kernel_warp(a, 1, e->stream);
+    else
+        launch_score_kernel(a, 1, e->threads, e->stream);
     CU(cudaGetLastError());
     long long cnt = 0;
     CU(cudaMemcpyAsync(&cnt, dn, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));

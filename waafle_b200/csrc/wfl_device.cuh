@@ -83,7 +83,8 @@ struct ScoreArgs {
     long long *dbg_count;
 };
 
-void launch_score_kernel(const ScoreArgs &a, int grid, int threads, cudaStream_t s);
+void launch_score_kernel(const ScoreArgs &a, int grid, int threads, cudaStream_t s);       // v1: CTA per contig
+void launch_score_kernel_warp(const ScoreArgs &a, int grid, cudaStream_t s);             // v2: warp per contig
 
 // Compaction (K10): CSR of melded members in contig order + contig indices grouped by call.
 struct CompactArgs {

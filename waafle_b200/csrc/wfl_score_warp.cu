@@ -1,0 +1,1464 @@
+// The per-contig scoring and clade-assignment kernel, revision 2 (sm_100a): ONE WARP PER CONTIG.
+//
+// Every CTA is a single warp that pulls contigs from a global work queue and runs the whole
+// reference block waafle/waafle_orgscorer.py:952-960 for each of them with warp-synchronous
+// primitives only (ballot / match / shuffle; no block barriers, no comparison sorts):
+//
+//   K1  hit x locus matching, records emitted locus-major by ballot ranking
+//                                       attach_hits / calc_overlap (waafle_orgscorer.py:359-369,
+//                                       559-564; utils.py:487-500)
+//   K3  annotation arg-max              waafle_orgscorer.py:384-392
+//   K5  taxonomy lift on the contig's distinct-clade table (parent gather + dedupe), records
+//       regrouped by one stable warp multisplit          waafle_orgscorer.py:431-445
+//   K2  envelope integral per (clade, locus) group in numpy's pairwise order, driven by a
+//       per-locus leaf plan shared by all clades     waafle_orgscorer.py:371-382,399-406
+//   K4  weak-loci mask / Unknown spike  waafle_orgscorer.py:407-429
+//   K6  one-clade search                waafle_orgscorer.py:447-461,495-509,585-597,621-631
+//   K7  two-clade pair search on gene bitmasks    waafle_orgscorer.py:511-545,599-619
+//   K8  ranking / meld / LGT filters    waafle_orgscorer.py:633-744, utils.py:401-411
+//   K9  level loop                      waafle_orgscorer.py:566-583
+//
+// Per-contig arrays come from a bump arena: the CTA's dynamic shared memory first, then a per-CTA
+// global slab (L2-resident), so 2-20-gene contigs live in shared memory and 100-kb contigs still
+// run.  fp64 throughout; the gene-score sums reproduce numpy's pairwise summation bit for bit
+// (constant leaves cost one memoised add chain per envelope run, leaves containing a breakpoint
+// are evaluated per accumulator column).
+#include "wfl_device.cuh"
+
+namespace wfl {
+
+namespace {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+constexpr u32 FULL = 0xffffffffu;
+constexpr int MAXDEPTH = 28;   // pairwise tree depth for n < 2^31
+constexpr int RMAX = 6;        // envelope runs handled per mixed leaf before the per-site fallback
+
+// Order-preserving map double -> u64 (max on the bits == max on the doubles).
+__device__ __forceinline__ u64 dbits(double x) {
+    if (x == 0.0) x = 0.0;   // -0.0 -> +0.0
+    u64 u = (u64)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dbits_inv(u64 b) {
+    u64 u = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+    return __longlong_as_double((long long)u);
+}
+
+struct Arena {
+    char *smem, *slab;
+    size_t smem_cap, slab_cap, smem_used, slab_used;
+    bool ok, all_smem;
+    __device__ __noinline__ void *raw(size_t bytes) {
+        bytes = (bytes + 15) & ~size_t(15);
+        if (smem_used + bytes <= smem_cap) {
+            void *p = smem + smem_used;
+            smem_used += bytes;
+            return p;
+        }
+        all_smem = false;
+        if (slab_used + bytes <= slab_cap) {
+            void *p = slab + slab_used;
+            slab_used += bytes;
+            return p;
+        }
+        ok = false;
+        return nullptr;
+    }
+    template <class T>
+    __device__ __forceinline__ T *get(size_t n) { return static_cast<T *>(raw(n * sizeof(T))); }
+};
+
+// ---- warp primitives -----------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lt_mask() { return (1u << lane_id()) - 1u; }
+
+__device__ __noinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __noinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 t = __shfl_xor_sync(FULL, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+__device__ __noinline__ long long warp_max_ll(long long v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        long long t = __shfl_xor_sync(FULL, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+__device__ __noinline__ int warp_excl_scan(int v, int &total) {
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL, inc, o);
+        if (lane_id() >= o) inc += t;
+    }
+    total = __shfl_sync(FULL, inc, 31);
+    return inc - v;
+}
+
+// LCA by depth-aligned parent walk == deepest common prefix of root-first lineages
+// (waafle/utils.py:401-411).  -1 is the identity.
+__device__ __noinline__ int lca2(const DevTax &t, int a, int b) {
+    if (a < 0) return b;
+    if (b < 0) return a;
+    int da = t.depth[a], db = t.depth[b];
+    while (da > db) { a = t.parent[a]; --da; }
+    while (db > da) { b = t.parent[b]; --db; }
+    while (a != b) { a = t.parent[a]; b = t.parent[b]; }
+    return a;
+}
+__device__ __noinline__ int warp_lca(const DevTax &t, int v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v = lca2(t, v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// Stable warp multisplit of `n` items by bin (bin_of(i) in [0, nbins)): out[] receives the item
+// indices grouped by bin, original order kept inside each bin.  `cur` is an nbins+1 scratch array;
+// on return cur[b] = end of bin b (== start of bin b+1).
+__device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, int *cur, int *out) {
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int b = lane; b <= nbins; b += 32) cur[b] = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        int b = i < n ? key[i] : nbins;
+        u32 peers = __match_any_sync(FULL, b);
+        if ((peers & lt_mask()) == 0) cur[b] += __popc(peers);
+        __syncwarp();
+    }
+    int carry = 0;
+#pragma unroll 1
+    for (int base = 0; base < nbins; base += 32) {
+        int b = base + lane, c = b < nbins ? cur[b] : 0, tot;
+        int ex = warp_excl_scan(c, tot);
+        if (b < nbins) cur[b] = carry + ex;
+        carry += tot;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        int b = i < n ? key[i] : nbins;
+        u32 peers = __match_any_sync(FULL, b);
+        if (i < n) out[cur[b] + __popc(peers & lt_mask())] = i;
+        __syncwarp();
+        if (i < n && (peers & lt_mask()) == 0) cur[b] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+// ---- numpy pairwise summation ---------------------------------------------------------------
+// numpy/_core/src/umath/loops_utils.h.src DOUBLE_pairwise_sum: n < 8 plain loop; n <= 128 eight
+// strided accumulators r[j] += a[i+j], res = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the n%8
+// tail; otherwise split at n2 = n/2 - (n/2)%8 and add the two halves.
+//
+// The split tree depends only on n, so it is flattened once per locus into a leaf plan shared by
+// all clades: plan entry = leaf size m | (#pending left sums to add after this leaf) << 8.
+
+// Emit (or just count, if plan == nullptr) the leaf plan of an n-element sum.
+__device__ __noinline__ int build_plan(int n, u16 *plan, u8 *k8set) {
+    int sz[MAXDEPTH], ch[MAXDEPTH], sp = 0, cnt = 0, nset = 0;
+    sz[0] = n;
+    ch[0] = 0;
+    sp = 1;
+    while (sp > 0) {
+        int m = sz[--sp], c = ch[sp];
+        if (m <= 128) {
+            if (plan) {
+                plan[cnt] = (u16)(m | (c << 8));
+                if (m >= 8 && nset <= 4) {   // distinct lane counts m/8, ascending, for the S_k memo
+                    u8 k = (u8)(m >> 3);
+                    int j = 0;
+                    while (j < nset && k8set[j] < k) ++j;
+                    if (j == nset || k8set[j] != k) {
+                        if (nset < 4) {
+#pragma unroll 1
+                            for (int q = nset; q > j; --q) k8set[q] = k8set[q - 1];
+                            k8set[j] = k;
+                        }
+                        ++nset;
+                    }
+                }
+            }
+            ++cnt;
+        } else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            sz[sp] = m - n2;   // right half: evaluated second, then added to the pending left sum
+            ch[sp++] = c + 1;
+            sz[sp] = n2;
+            ch[sp++] = 0;
+        }
+    }
+    if (plan) {
+#pragma unroll 1
+        for (int q = nset < 4 ? nset : 4; q < 4; ++q) k8set[q] = 0;
+        if (nset > 4) k8set[0] = k8set[1] = k8set[2] = k8set[3] = 0;   // too many sizes: no memo
+    }
+    return cnt;
+}
+
+// One (clade, locus) group: envelope of its records streamed as constant runs.
+struct Site {
+    const int *ord;       // record indices of the group, ord[rs..re)
+    const int *ra, *rb;   // python-slice [a, b) of each record inside the gene
+    const double *rv;     // waafle_score of each record
+    int rs, re, n;
+    bool sorted;          // records in descending score order -> first covering record is the max
+    int pos, run_end;
+    double run_v;
+    // memo of the add chains S_k(v) = v+v+...+v (k terms, sequential) for the current run
+    double Sk[4];
+    u8 k8[4];
+    bool memo_ok;
+
+    __device__ __forceinline__ void advance() {
+        double v = 0.0;   // np.zeros(len(locus)), waafle_orgscorer.py:381
+        int nx = n;
+#pragma unroll 1
+        for (int r = rs; r < re; ++r) {
+            int i = ord[r];
+            int a = ra[i], b = rb[i];
+            if (a <= pos && pos < b) {
+                v = fmax(v, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
+                nx = min(nx, b);
+                if (sorted) break;
+            } else if (a > pos) {
+                nx = min(nx, a);
+            }
+        }
+        run_v = v;
+        run_end = nx;
+        memo_ok = false;
+    }
+    __device__ __forceinline__ double next() {
+        if (pos >= run_end) advance();
+        ++pos;
+        return run_v;
+    }
+    // S_k(run_v) for k = m/8 lanes
+    __device__ __forceinline__ double chain(int k) {
+        const double v = run_v;
+        if (k8[0]) {
+            if (!memo_ok) {
+                double r = v;
+                int i = 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int kk = k8[j];
+#pragma unroll 1
+                    for (; i < kk; ++i) r += v;
+                    Sk[j] = r;
+                }
+                memo_ok = true;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k8[j] == k) return Sk[j];
+        }
+        double r = v;
+#pragma unroll 1
+        for (int i = 1; i < k; ++i) r += v;
+        return r;
+    }
+};
+
+// A leaf that lies inside one run.
+__device__ __forceinline__ double const_leaf(Site &s, int m) {
+    const double v = s.run_v;
+    s.pos += m;
+    if (v == 0.0) return 0.0;
+    double res;
+    if (m < 8) {
+        res = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < m; ++i) res += v;
+        return res;
+    }
+    res = 8.0 * s.chain(m >> 3);   // ((r+r)+(r+r))+((r+r)+(r+r)) with eight equal lanes: exact
+#pragma unroll 1
+    for (int i = 0; i < (m & 7); ++i) res += v;
+    return res;
+}
+
+// A leaf that contains envelope breakpoints.
+__device__ __forceinline__ double mixed_leaf(Site &s, int m) {
+    const int p0 = s.pos;
+    if (m < 8) {
+        double r = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < m; ++i) r += s.next();
+        return r;
+    }
+    // collect the runs that intersect the leaf (ends relative to the leaf start)
+    int rend[RMAX];
+    double rval[RMAX];
+    int nr = 0;
+    u32 brk = 0;   // (boundary & 7) of the interior run boundaries
+#pragma unroll 1
+    for (;;) {
+        if (s.pos >= s.run_end) s.advance();
+        int e = min(s.run_end - p0, m);
+        if (nr == RMAX) { nr = -1; break; }
+        rend[nr] = e;
+        rval[nr] = s.run_v;
+        ++nr;
+        if (e >= m) break;
+        brk |= 1u << (e & 7);
+        s.pos = p0 + e;
+    }
+    const int k8 = m >> 3, body = k8 << 3;
+    if (nr > 0) {
+        // column j accumulates a[j], a[8+j], ...: runs enter it as (count, value) stretches;
+        // neighbouring columns differ only where a run boundary b has b % 8 == j.  The eight
+        // column sums are folded into ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) as they appear.
+        double acc = 0.0, pair = 0.0, quad = 0.0, half = 0.0, res = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            if (j == 0 || ((brk >> j) & 1)) {
+                acc = 0.0;
+                bool first = true;
+                int start = 0;
+#pragma unroll 1
+                for (int q = 0; q < nr; ++q) {
+                    int e = min(rend[q], body);
+                    int c_lo = start <= j ? 0 : (start - j + 7) >> 3;
+                    int c_hi = e <= j ? 0 : (e - j + 7) >> 3;
+                    int cnt = c_hi - c_lo;
+                    start = rend[q];
+                    if (cnt <= 0) continue;
+                    const double v = rval[q];
+                    if (first) {
+                        acc = v;
+                        --cnt;
+                        first = false;
+                    }
+                    if (v != 0.0) {
+#pragma unroll 1
+                        for (int i = 0; i < cnt; ++i) acc += v;
+                    }
+                }
+            }
+            if ((j & 1) == 0) {
+                pair = acc;
+            } else {
+                pair = pair + acc;                       // r[j-1] + r[j]
+                if ((j & 2) == 0) {
+                    quad = pair;
+                } else {
+                    quad = quad + pair;                  // (r[j-3]+r[j-2]) + (r[j-1]+r[j])
+                    if (j == 3) half = quad; else res = half + quad;
+                }
+            }
+        }
+        int q = 0;
+#pragma unroll 1
+        for (int p = body; p < m; ++p) {   // the n % 8 tail of the last leaf
+            while (rend[q] <= p) ++q;
+            res += rval[q];
+        }
+        s.pos = p0 + m;
+        return res;
+    }
+    // more than RMAX runs in one leaf: literal per-site evaluation
+    s.pos = p0;
+    s.run_end = p0;
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = s.next();
+#pragma unroll 1
+    for (int c = 1; c < k8; ++c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += s.next();
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll 1
+    for (int p = body; p < m; ++p) res += s.next();
+    return res;
+}
+
+// np.mean of the group's site array (waafle_orgscorer.py:403) without materialising it.
+__device__ __noinline__ double group_mean(Site &s, const u16 *plan, int nleaf) {
+    double st[MAXDEPTH];
+    int sp = 0;
+    s.pos = 0;
+    s.run_end = 0;
+    s.memo_ok = false;
+#pragma unroll 1
+    for (int l = 0; l < nleaf; ++l) {
+        const int e = plan[l], m = e & 0xff, nadd = e >> 8;
+        if (s.pos >= s.run_end) s.advance();
+        double val = (s.run_end - s.pos >= m) ? const_leaf(s, m) : mixed_leaf(s, m);
+#pragma unroll 1
+        for (int q = 0; q < nadd; ++q) val = st[--sp] + val;
+        st[sp++] = val;
+    }
+    return st[0] / (double)s.n;
+}
+
+// Generic sequential pairwise sum for the short gene-level vectors of Contig.score.
+template <class Src>
+__device__ double pw_leaf_seq(Src &s, int m) {
+    if (m < 8) {
+        double r = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < m; ++i) r += s.next();
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = s.next();
+#pragma unroll 1
+    for (int c = 1; c < (m >> 3); ++c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += s.next();
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll 1
+    for (int i = 0; i < (m & 7); ++i) res += s.next();
+    return res;
+}
+template <class Src>
+__device__ double pairwise_seq(Src &s, int n) {
+    if (n <= 128) return pw_leaf_seq(s, n);
+    // explicit post-order walk of the split tree (only contigs with > 128 non-ignored loci get here)
+    int sz[MAXDEPTH];
+    double acc[MAXDEPTH];
+    u8 st[MAXDEPTH];
+    int sp = 0;
+    sz[0] = n;
+    st[0] = 0;
+    double ret = 0.0;
+    bool returning = false;
+#pragma unroll 1
+    for (;;) {
+        if (!returning) {
+            int m = sz[sp];
+            if (m <= 128) {
+                ret = pw_leaf_seq(s, m);
+                returning = true;
+                if (--sp < 0) break;
+            } else {
+                int n2 = m / 2;
+                n2 -= n2 % 8;
+                st[sp] = 1;
+                sz[sp + 1] = n2;
+                st[++sp] = 0;
+            }
+        } else if (st[sp] == 1) {
+            acc[sp] = ret;
+            int m = sz[sp], n2 = m / 2;
+            n2 -= n2 % 8;
+            st[sp] = 2;
+            sz[sp + 1] = m - n2;
+            st[++sp] = 0;
+            returning = false;
+        } else {
+            ret = acc[sp] + ret;
+            if (--sp < 0) break;
+        }
+    }
+    return ret;
+}
+
+// Gene-score rows are sparse: groups sorted by (clade, locus); a missing locus scores 0
+// (waafle_orgscorer.py:404-405).
+struct RowCursor {
+    const int *g_loc;
+    const double *g_score;
+    int p, e;
+    __device__ __forceinline__ double at(int locus) {
+        while (p < e && g_loc[p] < locus) ++p;
+        return (p < e && g_loc[p] == locus) ? g_score[p] : 0.0;
+    }
+};
+// Values of Contig.score (waafle_orgscorer.py:447-461): max(s1, s2) at the non-ignored loci.
+struct ScoreSrc {
+    RowCursor r1, r2;
+    const u8 *ign;
+    int i;
+    bool two;
+    double crit;
+    __device__ __forceinline__ double next() {
+        while (ign[i]) ++i;
+        double v = r1.at(i);
+        if (two) v = fmax(v, r2.at(i));
+        ++i;
+        crit = fmin(crit, v);
+        return v;
+    }
+};
+
+struct Level {   // per-level views shared by the search routines (all pointers arena-backed)
+    int G, W, T, Ngrp, n_unmasked;
+    const int *g_loc;
+    const double *g_score;
+    const int *cl_id, *cl_go;
+    const u64 *mk[3];   // per clade gene bitmasks: score >= k1 / k2 / c_eps
+    const u64 *um;      // non-ignored loci
+    const u8 *ign;
+    const int *l_len;
+};
+
+__device__ __noinline__ void score_clades(const Level &L, int t1, int t2, double &crit, double &rank) {
+    ScoreSrc s;
+    s.r1 = RowCursor{L.g_loc, L.g_score, L.cl_go[t1], L.cl_go[t1 + 1]};
+    s.two = t2 >= 0;
+    s.r2 = s.two ? RowCursor{L.g_loc, L.g_score, L.cl_go[t2], L.cl_go[t2 + 1]} : s.r1;
+    s.ign = L.ign;
+    s.i = 0;
+    s.crit = __longlong_as_double(0x7ff0000000000000ll);
+    double sum = pairwise_seq(s, L.n_unmasked);
+    crit = s.crit;
+    rank = sum / (double)L.n_unmasked;   // np.mean = add.reduce / n
+}
+
+// Letters of a two-clade option on word w (waafle_orgscorer.py:524-534), before the A/B swap.
+__device__ __forceinline__ void letters(const Level &L, const u64 *mamb, bool unknown_involved, int t1,
+                                        int t2, int w, u64 &A, u64 &B, u64 &amb) {
+    u64 um = L.um[w];
+    amb = unknown_involved ? 0ull : (mamb[(size_t)t1 * L.W + w] & mamb[(size_t)t2 * L.W + w] & um);
+    A = L.mk[1][(size_t)t1 * L.W + w] & um & ~amb;
+    B = L.mk[1][(size_t)t2 * L.W + w] & um & ~amb & ~A;
+}
+
+struct TwoEval {
+    bool swap, dir, ok;
+    int c1, c2, t1, t2;   // post-swap clade node ids / table positions
+};
+
+// set_synteny_two + apply_lgt_checks for one option (waafle_orgscorer.py:511-545, 678-744).
+__device__ __noinline__ void eval_two(const Level &L, const DevTax &tax, const DevParams &P, int ta, int tb,
+                                      TwoEval &ev) {
+    const u64 *mamb = L.mk[P.amb_sel], *msis = L.mk[P.sis_sel];
+    const bool unk = L.cl_id[ta] == tax.unknown || L.cl_id[tb] == tax.unknown;
+    bool swap = false;
+#pragma unroll 1
+    for (int w = 0; w < L.W; ++w) {   // "^[^A]*B": first clear letter is B -> swap
+        u64 A, B, amb;
+        letters(L, mamb, unk, ta, tb, w, A, B, amb);
+        u64 ab = A | B;
+        if (ab) {
+            u64 low = ab & (~ab + 1);
+            swap = (B & low) != 0;
+            break;
+        }
+    }
+    ev.swap = swap;
+    ev.t1 = swap ? tb : ta;
+    ev.t2 = swap ? ta : tb;
+    ev.c1 = L.cl_id[ev.t1];
+    ev.c2 = L.cl_id[ev.t2];
+    // one pass over the loci: lengths, counts, "^A+B+A+$" on the non-ignored letters
+    long long total_len = 0, amb_len = 0;
+    int nA = 0, nB = 0, state = 0;
+#pragma unroll 1
+    for (int w = 0; w < L.W; ++w) {
+        u64 A, B, amb;
+        letters(L, mamb, unk, ta, tb, w, A, B, amb);
+        if (swap) { u64 t = A; A = B; B = t; }
+        nA += __popcll(A);
+        nB += __popcll(B);
+        u64 bits = L.um[w];
+        while (bits) {
+            int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            u64 m = 1ull << b;
+            int len = L.l_len[w * 64 + b];
+            if (A & m) {
+                total_len += len;
+                state = (state == 0 || state == 1) ? 1 : (state == 2 || state == 3) ? 3 : -1;
+            } else if (B & m) {
+                total_len += len;
+                state = (state == 1 || state == 2) ? 2 : -1;
+            } else {
+                if (amb & m) { total_len += len; amb_len += len; }
+                state = -1;
+            }
+        }
+    }
+    ev.dir = state == 3;
+    bool ok = true;
+    if (total_len > 0 && (double)amb_len / (double)total_len > P.p.ambiguous_fraction) ok = false;
+    if (P.p.clade_genes >= 0 && min(nA, nB) < P.p.clade_genes) ok = false;
+    if (P.p.clade_leaves >= 0) {
+        int lc = ev.dir ? tax.leaf_count[ev.c2] : min(tax.leaf_count[ev.c1], tax.leaf_count[ev.c2]);
+        if (lc < P.p.clade_leaves) ok = false;
+    }
+    if (P.p.sister_penalty != 0 && ok) {
+        const int p1 = tax.parent[ev.c1], p2 = tax.parent[ev.c2];
+#pragma unroll 1
+        for (int t = 0; t < L.T && ok; ++t) {
+            int x = L.cl_id[t];
+            if (x == ev.c1 || x == ev.c2 || !tax.listed[x]) continue;
+            int px = tax.parent[x];
+            bool s1 = px == p1, s2 = (px == p2) && !ev.dir;
+            if (!s1 && !s2) continue;
+#pragma unroll 1
+            for (int w = 0; w < L.W; ++w) {
+                u64 A, B, amb;
+                letters(L, mamb, unk, ta, tb, w, A, B, amb);
+                if (swap) { u64 tt = A; A = B; B = tt; }
+                u64 ms = msis[(size_t)t * L.W + w];
+                // a B locus is penalised by clade1's sisters, an A locus by clade2's
+                if ((s1 && (ms & B)) || (s2 && (ms & A))) { ok = false; break; }
+            }
+        }
+    }
+    ev.ok = ok;
+}
+
+__device__ __noinline__ bool pair_pass(const Level &L, int t1, int t2) {
+    bool pass = true;   // crit >= k2  <=>  every non-ignored locus has s1 >= k2 or s2 >= k2
+#pragma unroll 1
+    for (int w = 0; w < L.W; ++w)
+        pass &= ((L.mk[1][(size_t)t1 * L.W + w] | L.mk[1][(size_t)t2 * L.W + w]) & L.um[w]) == L.um[w];
+    return pass;
+}
+
+__device__ __noinline__ void pair_decode(long long p, int n, int &i, int &j) {
+    // pairs enumerated i-major: (0,1),(0,2),...,(0,n-1),(1,2),...; offset(i) = i*(2n-i-1)/2
+    double nn = 2.0 * n - 1.0;
+    long long ii = (long long)floor((nn - sqrt(nn * nn - 8.0 * (double)p)) * 0.5);
+    if (ii < 0) ii = 0;
+    if (ii > n - 2) ii = n - 2;
+    while (ii > 0 && ii * (2LL * n - ii - 1) / 2 > p) --ii;
+    while ((ii + 1) * (2LL * n - ii - 2) / 2 <= p) ++ii;
+    i = (int)ii;
+    j = (int)(p - ii * (2LL * n - ii - 1) / 2) + i + 1;
+}
+
+// hit x locus test: scov / strand / calc_overlap >= --min-overlap (waafle_orgscorer.py:362-367)
+__device__ __noinline__ bool hit_matches(const DevParams &P, bool hit_ok, int hmin, int hmax, signed char hs,
+                                            int lmin, int llen, signed char ls) {
+    if (!hit_ok) return false;
+    if (P.p.stranded && hs != ls) return false;
+    int lmax = lmin + llen - 1;
+    double ov = 0.0;   // utils.py:492-499
+    if (!(lmin > hmax || hmin > lmax))
+        ov = (double)(min(hmax, lmax) - max(hmin, lmin) + 1) / (double)min(hmax - hmin + 1, llen);
+    return ov >= P.p.min_overlap;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// the kernel: blockDim.x == 32
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) {
+    extern __shared__ __align__(16) char smem_dyn[];
+    const int lane = threadIdx.x;
+    const DevParams &P = a.P;
+    const DevTax &tax = a.t;
+    const int S = P.p.n_systems;
+    const bool spike = P.p.weak_loci == 2;
+
+#pragma unroll 1
+    for (;;) {
+        long long c = -1;
+        if (lane == 0) {
+            unsigned long long w = atomicAdd(&a.ctr->next_work, 1ull);
+            c = (long long)w < a.n_work ? (a.work_list ? a.work_list[w] : (long long)w) : -1;
+        }
+        c = __shfl_sync(FULL, c, 0);
+        if (c < 0) break;
+
+        long long ph_last = clock64();
+        unsigned long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PH(i) do { if (lane == 0) { long long t_ = clock64(); ph[i] += (unsigned long long)(t_ - ph_last); ph_last = t_; } } while (0)
+
+        const long long h0 = a.b.hit_off[c], l0 = a.b.locus_off[c];
+        const int H = (int)(a.b.hit_off[c + 1] - h0), Graw = (int)(a.b.locus_off[c + 1] - l0);
+        Arena ar{smem_dyn, a.slab + (size_t)blockIdx.x * a.slab_bytes, (size_t)a.smem_bytes, a.slab_bytes,
+                 0, 0, true, true};
+        unsigned long long need_hint = 64ull * Graw + (1ull << 12);
+
+        // ---- loci: --min-gene-length filter, GFF order kept (waafle_orgscorer.py:348-352) ----
+        int *l_lo = ar.get<int>(Graw), *l_len = ar.get<int>(Graw), *l_raw = ar.get<int>(Graw);
+        int *l_base = ar.get<int>(Graw + 2);   // record range of each locus (locus-major records)
+        int *l_poff = ar.get<int>(Graw + 1);   // leaf-plan range of each locus
+        signed char *l_str = ar.get<signed char>(Graw);
+        u8 *l_k8 = ar.get<u8>(4 * (size_t)Graw);
+        bool overflow = !ar.ok;
+        int G = 0;
+#pragma unroll 1
+        for (int base = 0; base < Graw && !overflow; base += 32) {
+            int j = base + lane, flag = 0, lo = 0, len = 0;
+            if (j < Graw) {
+                int s = a.b.locus_start[l0 + j], e = a.b.locus_end[l0 + j];
+                lo = min(s, e);
+                len = max(s, e) - lo + 1;
+                flag = (double)len >= P.p.min_gene_length;
+                a.o.locus_flags[l0 + j] = flag ? WFL_LOCUS_RETAINED : 0;
+                a.o.synteny[l0 + j] = 0;
+#pragma unroll 1
+                for (int s2 = 0; s2 < S; ++s2) a.o.ann_winner[(l0 + j) * S + s2] = -1;
+            }
+            u32 m = __ballot_sync(FULL, flag);
+            if (flag) {
+                int pos = G + __popc(m & lt_mask());
+                l_lo[pos] = lo;
+                l_len[pos] = len;
+                l_raw[pos] = j;
+                l_str[pos] = a.b.locus_strand[l0 + j];
+            }
+            G += __popc(m);
+        }
+        __syncwarp();
+        const int W = (G + 63) >> 6;
+        int lifts = H > 0 ? P.p.jump_taxonomy : 0;
+        int r_call = WFL_CALL_UNCLASSIFIED, r_dir = 0, r_c1 = -1, r_c2 = -1, r_lca = -1, r_b1 = -1, r_b2 = -1,
+            r_na = 0, r_nb = 0, r_status = 0;
+        long long r_mem = 0;
+        double r_crit = 0.0, r_rank = 0.0;
+
+        if (!overflow && H > 0 && G > 0) {
+            // ---- K1 pass 1: matches per locus (ballot counts) + leaf-plan sizes ------------------
+#pragma unroll 1
+            for (int i = lane; i <= G + 1; i += 32) l_base[i] = 0;
+            int np_tot = 0;
+#pragma unroll 1
+            for (int base = 0; base < G; base += 32) {
+                int i = base + lane, np = 0;
+                if (i < G) np = build_plan(l_len[i], nullptr, nullptr);
+                int tot, ex = warp_excl_scan(np, tot);
+                if (i < G) l_poff[i] = np_tot + ex;
+                np_tot += tot;
+            }
+            if (lane == 0) l_poff[G] = np_tot;
+            __syncwarp();
+#pragma unroll 1
+            for (int base = 0; base < H; base += 32) {
+                int h = base + lane;
+                bool hok = false;
+                int hmin = 0, hmax = 0;
+                signed char hs = 0;
+                if (h < H) {
+                    hok = a.b.hit_scov[h0 + h] >= P.p.min_scov;   // waafle_orgscorer.py:362
+                    int q1 = a.b.hit_qstart[h0 + h], q2 = a.b.hit_qend[h0 + h];
+                    hmin = min(q1, q2);
+                    hmax = max(q1, q2);
+                    hs = a.b.hit_strand[h0 + h];
+                }
+                if (!__any_sync(FULL, hok)) continue;
+#pragma unroll 1
+                for (int i = 0; i < G; ++i) {
+                    u32 m = __ballot_sync(FULL, hit_matches(P, hok, hmin, hmax, hs, l_lo[i], l_len[i], l_str[i]));
+                    if (lane == 0 && m) l_base[i + 1] += __popc(m);
+                }
+            }
+            __syncwarp();
+            int M = 0;
+#pragma unroll 1
+            for (int base = 0; base < G; base += 32) {   // exclusive scan -> record base of each locus
+                int i = base + lane, cnt = i < G ? l_base[i + 1] : 0, tot;
+                int ex = warp_excl_scan(cnt, tot);
+                __syncwarp();
+                if (i < G) l_base[i + 1] = M + ex;   // cursor of locus i lives in l_base[i+1] during the fill
+                M += tot;
+            }
+            __syncwarp();
+            // worst case for this contig (groups <= M + G, clades <= groups + 1): one replay suffices
+            need_hint = 96ull * Graw + 2ull * np_tot + 40ull * (unsigned long long)M +
+                        48ull * ((unsigned long long)M + G + 2) +
+                        (80ull + 24ull * W) * ((unsigned long long)M + G + 2) + 16ull * (2 * M + 64) +
+                        (unsigned long long)G * (64 + 16 * S) + (1ull << 12);
+
+            // ---- record arrays (locus-major) ------------------------------------------------------
+            u16 *plan = ar.get<u16>(np_tot);
+            double *r_v = ar.get<double>(M);
+            int *r_a = ar.get<int>(M), *r_b = ar.get<int>(M), *r_t = ar.get<int>(M), *r_loc = ar.get<int>(M),
+                *r_hit = S > 0 ? ar.get<int>(M) : nullptr;
+            double *maxv = ar.get<double>(G);
+            u64 *maxb = ar.get<u64>(G);
+            u8 *ign = ar.get<u8>(G + 1);
+            u64 *um = ar.get<u64>(W);
+            u64 *annb = S > 0 ? ar.get<u64>((size_t)G * S) : nullptr;
+            int *annw = S > 0 ? ar.get<int>((size_t)G * S) : nullptr;
+            overflow = !ar.ok;
+            if (!overflow) {
+#pragma unroll 1
+                for (int i = lane; i < G; i += 32) build_plan(l_len[i], plan + l_poff[i], l_k8 + 4 * i);
+#pragma unroll 1
+                for (int i = lane; i < G * S; i += 32) { annb[i] = 0; annw[i] = -1; }
+                __syncwarp();
+                // ---- K1 pass 2: emit records (score_hit, waafle_orgscorer.py:371-382) -------------
+#pragma unroll 1
+                for (int base = 0; base < H; base += 32) {
+                    int h = base + lane;
+                    bool hok = false;
+                    int hmin = 0, hmax = 0, cl = 0;
+                    signed char hs = 0;
+                    double sc = 0.0;
+                    u32 sys = 0;
+                    if (h < H) {
+                        hok = a.b.hit_scov[h0 + h] >= P.p.min_scov;
+                        int q1 = a.b.hit_qstart[h0 + h], q2 = a.b.hit_qend[h0 + h];
+                        hmin = min(q1, q2);
+                        hmax = max(q1, q2);
+                        hs = a.b.hit_strand[h0 + h];
+                    }
+                    if (!__any_sync(FULL, hok)) continue;
+                    if (hok) {
+                        cl = a.b.hit_taxon[h0 + h];
+#pragma unroll 1
+                        for (int j = 0; j < P.p.jump_taxonomy; ++j) cl = tax.parent[cl];
+                        sc = a.b.hit_score[h0 + h];
+                        if (S > 0) sys = a.b.hit_sysmask[h0 + h];
+                    }
+#pragma unroll 1
+                    for (int i = 0; i < G; ++i) {
+                        const int lmin = l_lo[i], len = l_len[i];
+                        bool mt = hit_matches(P, hok, hmin, hmax, hs, lmin, len, l_str[i]);
+                        u32 m = __ballot_sync(FULL, mt);
+                        if (!m) continue;
+                        int cur = l_base[i + 1];
+                        if (mt) {
+                            int slot = cur + __popc(m & lt_mask());
+                            // python slice [h1 : h2+1] of a length-len array (:376-382)
+                            int s1 = max(0, hmin - lmin), e1 = min(len - 1, hmax - lmin) + 1;
+                            if (e1 < 0) e1 = max(0, e1 + len);
+                            s1 = min(s1, len);
+                            if (e1 < s1) e1 = s1;
+                            r_v[slot] = sc;
+                            r_a[slot] = s1;
+                            r_b[slot] = e1;
+                            r_t[slot] = cl;
+                            r_loc[slot] = i;
+                            if (S > 0) {
+                                r_hit[slot] = h;
+                                // K3 phase 1: max annotated score per (locus, system)
+                                u32 ms = sys;
+                                if (ms && sc >= P.ann_thr) {
+                                    u64 sb = dbits(sc);
+                                    while (ms) {
+                                        int s2 = __ffs(ms) - 1;
+                                        ms &= ms - 1;
+                                        atomicMax(&annb[(size_t)i * S + s2], sb);
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) l_base[i + 1] = cur + __popc(m);
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                // after the fill, l_base[i+1] == end of locus i == start of locus i+1; l_base[0] == 0
+                if (S > 0) {
+                    // K3 phase 2: the LAST hit (file order) attaining the max wins (:389, '>=')
+#pragma unroll 1
+                    for (int r = lane; r < M; r += 32) {
+                        u32 ms = a.b.hit_sysmask[h0 + r_hit[r]];
+                        double sc = r_v[r];
+                        if (ms && sc >= P.ann_thr) {
+                            u64 sb = dbits(sc);
+                            while (ms) {
+                                int s2 = __ffs(ms) - 1;
+                                ms &= ms - 1;
+                                if (annb[(size_t)r_loc[r] * S + s2] == sb)
+                                    atomicMax(&annw[(size_t)r_loc[r] * S + s2], r_hit[r]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int i = lane; i < G * S; i += 32) {
+                        int w = annw[i];
+                        a.o.ann_winner[(l0 + l_raw[i / S]) * S + (i % S)] = w >= 0 ? (int)(h0 + w) : -1;
+                    }
+                }
+                PH(0);
+
+                // ---- distinct clades of the contig: hash-dedupe + rank by counting ----------------
+                // cl_id[0..T) ascending; r_t[r] becomes the rank of the record's clade.  Lifts then
+                // work on this table (T parent gathers), not on the records.
+                int T = 0;
+                int *cl_id = ar.get<int>(M + 2);   // capacity for all levels (T never grows)
+                int *ord = ar.get<int>(M);
+                int *map_t = ar.get<int>(M + 2);
+                u8 *fo = ar.get<u8>(M + 2);
+                const size_t mark_smem = ar.smem_used, mark_slab = ar.slab_used;
+                {
+                    int cap = 64;
+                    while (cap < 2 * (M + 1)) cap <<= 1;
+                    int *hk = ar.get<int>(cap), *hv = ar.get<int>(cap);
+                    int *dl = ar.get<int>(M + 1);
+                    if (!ar.ok) overflow = true;
+                    if (!overflow) {
+#pragma unroll 1
+                        for (int i = lane; i < cap; i += 32) hk[i] = -1;
+                        __syncwarp();
+#pragma unroll 1
+                        for (int r = lane; r < M + (spike ? 1 : 0); r += 32) {
+                            int key = r < M ? r_t[r] : tax.unknown;
+                            u32 slot = ((u32)key * 2654435761u) & (cap - 1);
+#pragma unroll 1
+                            for (;;) {
+                                int old = atomicCAS(&hk[slot], -1, key);
+                                if (old == -1 || old == key) break;
+                                slot = (slot + 1) & (cap - 1);
+                            }
+                            if (r < M) r_t[r] = (int)slot;
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int base = 0; base < cap; base += 32) {   // compact the distinct keys
+                            int i = base + lane;
+                            bool f = hk[i] >= 0;
+                            u32 m = __ballot_sync(FULL, f);
+                            if (f) dl[T + __popc(m & lt_mask())] = i;
+                            T += __popc(m);
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int j = lane; j < T; j += 32) {   // rank = #distinct keys below
+                            int key = hk[dl[j]], rk = 0;
+#pragma unroll 1
+                            for (int q = 0; q < T; ++q) rk += hk[dl[q]] < key;
+                            hv[dl[j]] = rk;
+                            cl_id[rk] = key;
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int r = lane; r < M; r += 32) r_t[r] = hv[r_t[r]];
+                        __syncwarp();
+                    }
+                }
+                PH(1);
+
+                // ---- K9: level loop (evaluate_contig, waafle_orgscorer.py:566-583) ----------------
+                int n_levels = 0;
+                long long n_groups = 0, n_ptest = 0, n_pscore = 0;
+#pragma unroll 1
+                for (int iter = 0; !overflow; ++iter) {
+                    ar.smem_used = mark_smem;
+                    ar.slab_used = mark_slab;
+                    ++n_levels;
+                    // ---- regroup: stable multisplit of the locus-major records by clade rank ------
+                    int *cur = ar.get<int>(T + 2);
+                    if (!ar.ok) { overflow = true; break; }
+                    warp_multisplit(M, T, r_t, cur, ord);
+                    __syncwarp();
+                    // groups = maximal runs of equal (clade rank, locus) in ord
+                    int t_unk = -1;
+                    if (spike) {
+                        int lo = 0, hi = T;   // cl_id ascending: binary search for Unknown
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (cl_id[mid] < tax.unknown) lo = mid + 1; else hi = mid;
+                        }
+                        t_unk = lo;   // present by construction (inserted before ranking / kept by lifts)
+                    }
+                    int ng = 0, nlt = 0, nu = 0;
+#pragma unroll 1
+                    for (int base = 0; base < M; base += 32) {
+                        int r = base + lane;
+                        bool f = false;
+                        int t = 0;
+                        if (r < M) {
+                            int i = ord[r];
+                            t = r_t[i];
+                            f = r == 0 || t != r_t[ord[r - 1]] || r_loc[i] != r_loc[ord[r - 1]];
+                        }
+                        ng += __popc(__ballot_sync(FULL, f));
+                        if (spike) {
+                            nlt += __popc(__ballot_sync(FULL, f && t < t_unk));
+                            nu += __popc(__ballot_sync(FULL, f && t == t_unk));
+                        }
+                    }
+                    const int Ngrp = spike ? ng - nu + G : ng;
+                    n_groups += Ngrp;
+                    double *g_score = ar.get<double>(Ngrp);
+                    int *g_rs = ar.get<int>(Ngrp + 1), *g_loc = ar.get<int>(Ngrp), *g_t = ar.get<int>(Ngrp),
+                        *g_perm = ar.get<int>(Ngrp), *gcur = ar.get<int>(G + 2);
+                    if (!ar.ok) { overflow = true; break; }
+                    int gbase = 0;
+#pragma unroll 1
+                    for (int base = 0; base < M; base += 32) {
+                        int r = base + lane;
+                        bool f = false;
+                        int t = 0, loc = 0;
+                        if (r < M) {
+                            int i = ord[r];
+                            t = r_t[i];
+                            loc = r_loc[i];
+                            f = r == 0 || t != r_t[ord[r - 1]] || loc != r_loc[ord[r - 1]];
+                        }
+                        u32 m = __ballot_sync(FULL, f);
+                        if (f) {
+                            int gid = gbase + __popc(m & lt_mask()), dst = gid;
+                            if (spike) dst = t < t_unk ? gid : (t == t_unk ? -1 : gid - nu + G);
+                            if (dst >= 0) {
+                                g_rs[dst] = r;
+                                g_loc[dst] = loc;
+                                g_t[dst] = t;
+                            }
+                        }
+                        gbase += __popc(m);
+                    }
+                    if (spike)
+                        for (int i = lane; i < G; i += 32) {
+                            g_rs[nlt + i] = -1;
+                            g_loc[nlt + i] = i;
+                            g_t[nlt + i] = t_unk;
+                        }
+#pragma unroll 1
+                    for (int i = lane; i < G; i += 32) maxb[i] = dbits(0.0);
+                    __syncwarp();
+                    PH(2);
+                    // ---- K2: envelope integral per group, numpy-pairwise-exact ----------------------
+                    // groups are visited locus-major so that the lanes of a warp walk the same leaf plan
+                    warp_multisplit(Ngrp, G, g_loc, gcur, g_perm);
+                    __syncwarp();
+#pragma unroll 1
+                    for (int base = 0; base < Ngrp; base += 32) {
+                        int gi = base + lane;
+                        if (gi < Ngrp) {
+                            int g = g_perm[gi];
+                            int rs = g_rs[g];
+                            if (rs >= 0) {
+                                const int t = g_t[g], loc = g_loc[g];
+                                int re = rs + 1;
+                                while (re < M && r_t[ord[re]] == t && r_loc[ord[re]] == loc) ++re;
+                                const int k = re - rs;
+                                bool sorted = false;
+                                if (k > 4) {   // order the group's records by descending score
+#pragma unroll 1
+                                    for (int x = rs + 1; x < re; ++x) {
+                                        int ix = ord[x];
+                                        double vx = r_v[ix];
+                                        int y = x - 1;
+                                        while (y >= rs && r_v[ord[y]] < vx) {
+                                            ord[y + 1] = ord[y];
+                                            --y;
+                                        }
+                                        ord[y + 1] = ix;
+                                    }
+                                    sorted = true;
+                                }
+                                Site s;
+                                s.ord = ord; s.ra = r_a; s.rb = r_b; s.rv = r_v;
+                                s.rs = rs; s.re = re; s.n = l_len[loc]; s.sorted = sorted;
+                                s.k8[0] = l_k8[4 * loc]; s.k8[1] = l_k8[4 * loc + 1];
+                                s.k8[2] = l_k8[4 * loc + 2]; s.k8[3] = l_k8[4 * loc + 3];
+                                double sc = group_mean(s, plan + l_poff[loc], l_poff[loc + 1] - l_poff[loc]);
+                                g_score[g] = sc;
+                                if (cl_id[t] != tax.unknown)   // waafle_orgscorer.py:409-411
+                                    atomicMax(&maxb[loc], dbits(sc));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    PH(3);
+                    // ---- K4: weak loci (waafle_orgscorer.py:412-427) ---------------------------------
+#pragma unroll 1
+                    for (int i = lane; i < G; i += 32) {
+                        double mx = dbits_inv(maxb[i]);
+                        maxv[i] = mx;
+                        ign[i] = (P.p.weak_loci == 0) ? !(mx >= P.min_thr) : 0;
+                        if (spike) g_score[nlt + i] = 1.0 - mx;
+                    }
+                    if (lane == 0) ign[G] = 0;   // sentinel for ScoreSrc
+                    __syncwarp();
+                    int nun = 0;
+#pragma unroll 1
+                    for (int w = lane; w < W; w += 32) {
+                        u64 m = 0;
+#pragma unroll 1
+                        for (int b = 0; b < 64 && w * 64 + b < G; ++b)
+                            if (!ign[w * 64 + b]) m |= 1ull << b;
+                        um[w] = m;
+                        nun += __popcll(m);
+                    }
+#pragma unroll 1
+                    for (int i = lane; i < G; i += 32)
+                        a.o.locus_flags[l0 + l_raw[i]] = WFL_LOCUS_RETAINED | (ign[i] ? WFL_LOCUS_IGNORED : 0);
+                    nun = warp_sum(nun);
+                    if (iter == 0 && c == a.dbg_contig) {
+#pragma unroll 1
+                        for (int g = lane; g < Ngrp; g += 32)
+                            if (g < a.dbg_cap) {
+                                a.dbg_clade[g] = cl_id[g_t[g]];
+                                a.dbg_locus[g] = g_loc[g];
+                                a.dbg_score[g] = g_score[g];
+                            }
+                        if (lane == 0) *a.dbg_count = Ngrp;
+                    }
+                    if (iter == 0 && nun == 0) break;   // "empty" contig, waafle_orgscorer.py:959
+
+                    // ---- clade rows + gene bitmasks ----------------------------------------------------
+                    // every rank in [0, T) owns >= 1 group (the spiked Unknown owns G)
+                    int *cl_go = ar.get<int>(T + 1), *cand = ar.get<int>(T);
+                    double *cl_rank = ar.get<double>(T), *cl_crit = ar.get<double>(T);
+                    u8 *cl_opt = ar.get<u8>(T), *memA = ar.get<u8>(T), *memB = ar.get<u8>(T);
+                    u64 *mk0 = ar.get<u64>((size_t)T * W), *mk1 = ar.get<u64>((size_t)T * W),
+                        *mk2 = ar.get<u64>((size_t)T * W);
+                    u64 *bestm = ar.get<u64>(3 * (size_t)W);
+                    if (!ar.ok) { overflow = true; break; }
+#pragma unroll 1
+                    for (int g = lane; g < Ngrp; g += 32)
+                        if (g == 0 || g_t[g] != g_t[g - 1]) cl_go[g_t[g]] = g;
+                    if (lane == 0) cl_go[T] = Ngrp;
+                    int hasroot = 0;
+#pragma unroll 1
+                    for (int t = lane; t < T; t += 32) hasroot |= cl_id[t] == tax.root;
+                    hasroot = __any_sync(FULL, hasroot);
+                    __syncwarp();
+#pragma unroll 1
+                    for (int t = lane; t < T; t += 32) {
+                        memA[t] = memB[t] = 0;
+#pragma unroll 1
+                        for (int q = 0; q < 3; ++q) {
+                            u64 *m = (q == 0 ? mk0 : q == 1 ? mk1 : mk2) + (size_t)t * W;
+                            const double thr = q == 0 ? P.p.k1 : q == 1 ? P.p.k2 : 1e-6;
+                            // a locus without an entry scores 0 (waafle_orgscorer.py:404-405)
+#pragma unroll 1
+                            for (int w = 0; w < W; ++w) {
+                                int nb = min(64, G - w * 64);
+                                m[w] = thr <= 0.0 ? (nb == 64 ? ~0ull : ((1ull << nb) - 1)) : 0ull;
+                            }
+#pragma unroll 1
+                            for (int g = cl_go[t]; g < cl_go[t + 1]; ++g) {
+                                int loc = g_loc[g];
+                                u64 bit = 1ull << (loc & 63);
+                                if (g_score[g] >= thr) m[loc >> 6] |= bit;
+                                else m[loc >> 6] &= ~bit;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    Level L{G, W, T, Ngrp, nun, g_loc, g_score, cl_id, cl_go, {mk0, mk1, mk2}, um, ign, l_len};
+                    PH(4);
+
+                    // ---- K6: one-clade search (explain_one, waafle_orgscorer.py:585-597) -----------
+                    u64 bbits = 0;
+#pragma unroll 1
+                    for (int t = lane; t < T; t += 32) {
+                        bool pass = true;
+#pragma unroll 1
+                        for (int w = 0; w < W; ++w) pass &= (mk0[(size_t)t * W + w] & um[w]) == um[w];   // crit >= k1
+                        cl_opt[t] = pass;
+                        if (pass) {
+                            double crit, rank;
+                            score_clades(L, t, -1, crit, rank);
+                            cl_rank[t] = rank;
+                            cl_crit[t] = crit;
+                            u64 b = dbits(rank);
+                            bbits = b > bbits ? b : bbits;
+                        }
+                    }
+                    bbits = warp_max_u64(bbits);
+                    __syncwarp();
+                    long long bt = -1;
+                    if (bbits)
+                        for (int t = lane; t < T; t += 32)
+                            if (cl_opt[t] && dbits(cl_rank[t]) == bbits) bt = t;   // ties: last in name order
+                    bt = warp_max_ll(bt);
+                    PH(5);
+                    if (bt >= 0) {
+                        // meld_one (waafle_orgscorer.py:621-631)
+                        const int tb = (int)bt;
+                        const double brank = cl_rank[tb];
+                        r_call = WFL_CALL_NO_LGT;
+                        r_b1 = r_c1 = cl_id[tb];
+                        r_crit = cl_crit[tb];
+                        r_rank = brank;
+                        if (P.p.disambiguate_one == 1) {
+                            int my = -1, nk = 0;
+#pragma unroll 1
+                            for (int t = lane; t < T; t += 32)
+                                if (cl_opt[t] && brank - cl_rank[t] <= P.p.range) {
+                                    my = lca2(tax, my, cl_id[t]);
+                                    memA[t] = 1;
+                                    ++nk;
+                                }
+                            r_c1 = warp_lca(tax, my);
+                            r_na = warp_sum(nk);
+                        }
+#pragma unroll 1
+                        for (int i = lane; i < G; i += 32)   // set_synteny_one (:495-509)
+                            a.o.synteny[l0 + l_raw[i]] =
+                                ign[i] ? '~' : ((mk0[(size_t)tb * W + (i >> 6)] >> (i & 63)) & 1 ? 'A' : '!');
+                    } else {
+                        // ---- K7: two-clade search (explain_two, waafle_orgscorer.py:599-619) --------
+                        int T2 = 0;
+#pragma unroll 1
+                        for (int base = 0; base < T; base += 32) {
+                            int t = base + lane;
+                            bool f = false;
+                            if (t < T)   // max(gene_scores[clade]) >= k2, unmasked (:603-605)
+                                for (int w = 0; w < W; ++w) f |= mk1[(size_t)t * W + w] != 0;
+                            u32 m = __ballot_sync(FULL, f);
+                            if (f) cand[T2 + __popc(m & lt_mask())] = t;
+                            T2 += __popc(m);
+                        }
+                        __syncwarp();
+                        const long long NP = (long long)T2 * (T2 - 1) / 2;
+                        n_ptest += NP;
+                        // pass 1: best rank; ties -> last pair in (clade1, clade2) iteration order
+                        double my_rank = -1.0;
+                        long long my_p = -1;
+                        int nsc = 0;
+#pragma unroll 1
+                        for (long long p = lane; p < NP; p += 32) {
+                            int i, j;
+                            pair_decode(p, T2, i, j);
+                            int t1 = cand[i], t2 = cand[j];
+                            if (!pair_pass(L, t1, t2)) continue;   // crit < k2 (:610)
+                            ++nsc;
+                            double crit, rank;
+                            score_clades(L, t1, t2, crit, rank);
+                            if (my_p < 0 || rank >= my_rank) { my_rank = rank; my_p = p; }
+                        }
+                        n_pscore += warp_sum(nsc);
+                        u64 pb = warp_max_u64(my_p >= 0 ? dbits(my_rank) : 0ull);
+                        const long long bp = warp_max_ll((my_p >= 0 && dbits(my_rank) == pb) ? my_p : -1);
+                        if (bp >= 0) {
+                            // meld_two (waafle_orgscorer.py:633-669)
+                            int bi, bj;
+                            pair_decode(bp, T2, bi, bj);
+                            TwoEval be;
+                            eval_two(L, tax, P, cand[bi], cand[bj], be);
+                            double bcrit, brank;
+                            score_clades(L, cand[bi], cand[bj], bcrit, brank);
+                            const bool bunk = be.c1 == tax.unknown || be.c2 == tax.unknown;
+#pragma unroll 1
+                            for (int w = lane; w < W; w += 32) {
+                                u64 A, Bm, amb;
+                                letters(L, L.mk[P.amb_sel], bunk, cand[bi], cand[bj], w, A, Bm, amb);
+                                bestm[w] = be.swap ? Bm : A;
+                                bestm[W + w] = be.swap ? A : Bm;
+                                bestm[2 * W + w] = amb;
+                            }
+                            __syncwarp();
+                            int nk = 0, nbad = 0, ndiff = 0, la = -1, lb = -1;
+#pragma unroll 1
+                            for (long long p = lane; p < NP; p += 32) {
+                                int i, j;
+                                pair_decode(p, T2, i, j);
+                                int t1 = cand[i], t2 = cand[j];
+                                if (!pair_pass(L, t1, t2)) continue;
+                                double crit, rank;
+                                score_clades(L, t1, t2, crit, rank);
+                                if (!(brank - rank <= P.p.range)) continue;   // :636
+                                TwoEval ev;
+                                eval_two(L, tax, P, t1, t2, ev);
+                                ++nk;
+                                nbad += !ev.ok;
+                                const bool unk = ev.c1 == tax.unknown || ev.c2 == tax.unknown;
+                                bool same = true;   // meld_precheck: same synteny string (:671-676)
+#pragma unroll 1
+                                for (int w = 0; w < W; ++w) {
+                                    u64 A, Bm, amb;
+                                    letters(L, L.mk[P.amb_sel], unk, t1, t2, w, A, Bm, amb);
+                                    same &= (ev.swap ? Bm : A) == bestm[w] && (ev.swap ? A : Bm) == bestm[W + w] &&
+                                            amb == bestm[2 * W + w];
+                                }
+                                ndiff += !same;
+                                la = lca2(tax, la, ev.c1);
+                                lb = lca2(tax, lb, ev.c2);
+                                memA[ev.t1] = 1;
+                                memB[ev.t2] = 1;
+                            }
+                            nk = warp_sum(nk);
+                            nbad = warp_sum(nbad);
+                            ndiff = warp_sum(ndiff);
+                            la = warp_lca(tax, la);
+                            lb = warp_lca(tax, lb);
+                            __syncwarp();
+                            bool have = true, melded = false;
+                            int c1 = be.c1, c2 = be.c2;
+                            if (nk == 1 || P.p.disambiguate_two == 0) {
+                            } else if (P.p.disambiguate_two == 1) {
+                                have = false;
+                            } else if (nbad > 0 || ndiff > 0) {
+                                have = false;
+                            } else {
+                                c1 = la;
+                                c2 = lb;
+                                melded = true;
+                                if (!P.p.allow_lca) {   // post-meld LCA check (:661-665)
+                                    int l = lca2(tax, c1, c2);
+                                    if (l == c1 || l == c2) have = false;
+                                }
+                            }
+                            if (have && be.ok) {
+                                r_call = WFL_CALL_LGT;
+                                r_b1 = be.c1;
+                                r_b2 = be.c2;
+                                r_c1 = c1;
+                                r_c2 = c2;
+                                r_lca = lca2(tax, c1, c2);   // waafle_orgscorer.py:882
+                                r_crit = bcrit;
+                                r_rank = brank;
+                                r_dir = be.dir;
+                                if (melded) {
+                                    int na = 0, nb = 0;
+#pragma unroll 1
+                                    for (int t = lane; t < T; t += 32) { na += memA[t]; nb += memB[t]; }
+                                    r_na = warp_sum(na);
+                                    r_nb = warp_sum(nb);
+                                }
+#pragma unroll 1
+                                for (int i = lane; i < G; i += 32) {
+                                    u64 m = 1ull << (i & 63);
+                                    int w = i >> 6;
+                                    a.o.synteny[l0 + l_raw[i]] = ign[i] ? '~' : (bestm[2 * W + w] & m) ? '*'
+                                                                 : (bestm[w] & m) ? 'A' : (bestm[W + w] & m) ? 'B' : '!';
+                                }
+                            }
+                        }
+                    }
+                    PH(6);
+                    if (r_call != WFL_CALL_UNCLASSIFIED) {
+                        // ---- melded members -> staging pool (tails, waafle_orgscorer.py:630,658-659)
+                        if (r_na + r_nb > 0) {
+                            long long mb = 0;
+                            if (lane == 0)
+                                mb = (long long)atomicAdd(&a.ctr->mem_pool_used, (unsigned long long)(r_na + r_nb));
+                            r_mem = __shfl_sync(FULL, mb, 0);
+#pragma unroll 1
+                            for (int side = 0; side < 2; ++side) {
+                                const u8 *mem = side ? memB : memA;
+                                long long off = r_mem + (side ? r_na : 0);
+                                if ((side ? r_nb : r_na) == 0) continue;
+                                int mbase = 0;
+#pragma unroll 1
+                                for (int base = 0; base < T; base += 32) {
+                                    int t = base + lane;
+                                    bool f = t < T && mem[t];
+                                    u32 m = __ballot_sync(FULL, f);
+                                    long long dst = off + mbase + __popc(m & lt_mask());
+                                    if (f && dst < a.o.mem_pool_cap) a.o.mem_pool[dst] = cl_id[t];
+                                    mbase += __popc(m);
+                                }
+                            }
+                        }
+                        break;
+                    }
+                    // not explained at this level: stop or lift (waafle_orgscorer.py:571-575)
+                    if (T == 0 || hasroot) break;
+                    if (iter >= 100) { r_status = 2; break; }   // :580-581
+                    // ---- K5: lift the distinct-clade table (raise_taxonomy, :431-445) ----------------
+                    // parents of the T clades, deduped and re-ranked (rank by counting); records follow
+                    // through map_t.  "Unknown" spiked at this level is not a site-score clade: it is
+                    // dropped here and re-inserted (:418, :433-443).
+                    {
+                        int *par = ar.get<int>(T + 1);
+                        if (!ar.ok) { overflow = true; break; }
+                        bool rec_unknown = false;   // does a record clade equal Unknown? (hit taxon named so)
+                        if (spike) rec_unknown = nu > 0;
+#pragma unroll 1
+                        for (int t = lane; t < T; t += 32) {
+                            bool drop = spike && t == t_unk && !rec_unknown;
+                            par[t] = drop ? -1 : tax.parent[cl_id[t]];
+                        }
+                        if (lane == 0) par[T] = spike ? tax.unknown : -1;   // re-inserted spike key
+                        __syncwarp();
+                        int Tn = 0;
+#pragma unroll 1
+                        for (int base = 0; base <= T; base += 32) {   // first occurrences of each key
+                            int t = base + lane;
+                            bool f = false;
+                            if (t <= T && par[t] >= 0) {
+                                f = true;
+#pragma unroll 1
+                                for (int z = 0; z < t; ++z)
+                                    if (par[z] == par[t]) { f = false; break; }
+                            }
+                            if (t <= T) fo[t] = f;
+                            Tn += __popc(__ballot_sync(FULL, f));
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int t = lane; t <= T; t += 32) {   // rank = #distinct keys below
+                            int key = par[t], rk = -1;
+                            if (key >= 0) {
+                                rk = 0;
+#pragma unroll 1
+                                for (int q = 0; q <= T; ++q) rk += fo[q] && par[q] < key;
+                            }
+                            map_t[t] = rk;
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int r = lane; r < M; r += 32) r_t[r] = map_t[r_t[r]];
+                        __syncwarp();
+#pragma unroll 1
+                        for (int t = lane; t <= T; t += 32)
+                            if (map_t[t] >= 0) cl_id[map_t[t]] = par[t];   // equal keys write equal values
+                        T = Tn;
+                        __syncwarp();
+                    }
+                    ++lifts;
+                    PH(7);
+                }
+                PH(8);
+                if (lane == 0) {
+#pragma unroll 1
+                    for (int q = 0; q < 9; ++q) atomicAdd(&a.ctr->phase_cycles[q], ph[q]);
+                    atomicAdd(&a.ctr->matched_pairs, (unsigned long long)M);
+                    atomicAdd(&a.ctr->groups, (unsigned long long)n_groups);
+                    atomicAdd(&a.ctr->levels, (unsigned long long)n_levels);
+                    if (n_ptest) atomicAdd(&a.ctr->pairs_tested, (unsigned long long)n_ptest);
+                    if (n_pscore) atomicAdd(&a.ctr->pairs_scored, (unsigned long long)n_pscore);
+                    if (ar.all_smem && !overflow) atomicAdd(&a.ctr->smem_contigs, 1ull);
+                }
+            }
+        }
+
+        if (overflow) {
+            // replay with a larger slab: report a worst-case byte count for this contig
+            r_status = 1;
+            r_call = WFL_CALL_UNCLASSIFIED;
+            if (lane == 0) {
+                atomicMax(&a.ctr->slab_need_max, need_hint);
+                atomicAdd(&a.ctr->n_overflow, 1ull);
+            }
+        }
+        if (lane == 0) {
+            if (r_status == 2) atomicAdd(&a.ctr->n_runaway, 1ull);
+            a.o.call[c] = (uint8_t)r_call;
+            a.o.direction[c] = (uint8_t)r_dir;
+            a.o.lifts[c] = lifts;
+            a.o.clade1[c] = r_c1;
+            a.o.clade2[c] = r_c2;
+            a.o.lca[c] = r_lca;
+            a.o.best1[c] = r_b1;
+            a.o.best2[c] = r_b2;
+            a.o.crit[c] = r_crit;
+            a.o.rank[c] = r_rank;
+            a.o.n_mem_a[c] = r_na;
+            a.o.n_mem_b[c] = r_nb;
+            a.o.mem_pos[c] = r_mem;
+            a.o.status[c] = (uint8_t)r_status;
+        }
+        __syncwarp();
+    }
+}
+
+void launch_score_kernel_warp(const ScoreArgs &a, int grid, cudaStream_t s) {
+    cudaFuncSetAttribute(wfl_score_contigs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    wfl_score_contigs_warp<<<grid, 32, a.smem_bytes, s>>>(a);
+}
+
+}  // namespace wfl
