@@ -133,7 +133,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = {"cfg2": 60, "cfg3": 25, "cfg5": 25, "cfg4": 1}.get(args.workload, 30)
+    per_core = {"cfg2": 400, "cfg3": 150, "cfg5": 150, "cfg4": 2}.get(args.workload, 100)
     n_sample = args.cpu_sample or cores * per_core
     args.contigs = args.contigs or None
     a2 = argparse.Namespace(**vars(args))
@@ -186,7 +186,7 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        per_core = {"cfg2": 60, "cfg3": 25, "cfg5": 25, "cfg4": 1}.get(args.workload, 30)
+        per_core = {"cfg2": 1500, "cfg3": 600, "cfg5": 600, "cfg4": 4}.get(args.workload, 300)
         n_sample = args.cpu_sample or cores * per_core
         rate, wall, used, _ = cpu_baseline_run(batch, params, tax, n_sample, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",

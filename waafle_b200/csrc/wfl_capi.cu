@@ -24,8 +24,10 @@ struct wfl_engine {
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> chunk_ev;
+    size_t chunk_bytes = size_t(48) << 20;   // H2D chunk size of the pipelined plugin call
     std::string err;
     bool have_params = false, have_tax = false, have_batch = false, have_results = false;
     DevParams P{};
@@ -38,7 +40,8 @@ struct wfl_engine {
     int threads = 32, smem_bytes = 14 * 1024, ctas_per_sm = 12;
     size_t slab_bytes = 128 * 1024;
     // device buffers (grow-only)
-    Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4];
+    Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
+    int plan_nmax = 0;
     wfl_stats stats{};
     int64_t members_total = 0;
 };
@@ -93,6 +96,68 @@ int outbuf(wfl_engine *e, Buf &b, size_t n, T **dst) {
     return WFL_OK;
 }
 
+
+// Host twin of the kernel's build_plan(): numpy's pairwise split tree over n elements, flattened
+// (numpy/_core/src/umath/loops_utils.h.src: leaves <= 128, split at n/2 - (n/2) % 8).
+void host_build_plan(int n, std::vector<uint16_t> &data, PlanEntry &pe) {
+    pe.off = (uint32_t)data.size();
+    int sz[64], ch[64], sp = 0, nset = 0;
+    uint8_t k8[5] = {0, 0, 0, 0, 0};
+    sz[0] = n;
+    ch[0] = 0;
+    sp = 1;
+    uint32_t cnt = 0;
+    while (sp > 0) {
+        int m = sz[--sp], c = ch[sp];
+        if (m <= 128) {
+            data.push_back((uint16_t)(m | (c << 8)));
+            ++cnt;
+            if (m >= 8 && nset <= 4) {
+                uint8_t k = (uint8_t)(m >> 3);
+                int j = 0;
+                while (j < nset && j < 4 && k8[j] < k) ++j;
+                if (j == nset || (j < 4 && k8[j] != k)) {
+                    if (nset < 4) {
+                        for (int q = nset; q > j; --q) k8[q] = k8[q - 1];
+                        k8[j] = k;
+                    }
+                    ++nset;
+                }
+            }
+        } else {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            sz[sp] = m - n2;
+            ch[sp++] = c + 1;
+            sz[sp] = n2;
+            ch[sp++] = 0;
+        }
+    }
+    pe.nleaf = cnt;
+    if (nset > 4) k8[0] = k8[1] = k8[2] = k8[3] = 0;
+    pe.k8 = (uint32_t)k8[0] | ((uint32_t)k8[1] << 8) | ((uint32_t)k8[2] << 16) | ((uint32_t)k8[3] << 24);
+}
+
+// Leaf plans for every gene length up to `want` (capped): built once, kept on the device.
+int ensure_plan_table(wfl_engine *e, int want) {
+    const int cap = 16384;
+    want = std::min(std::max(want, 4096), cap);
+    if (e->plan_nmax >= want) return WFL_OK;
+    std::vector<PlanEntry> index((size_t)want + 1);
+    std::vector<uint16_t> data;
+    data.reserve((size_t)want * want / 150 + 1024);
+    index[0] = PlanEntry{0, 0, 0};
+    for (int n = 1; n <= want; ++n) host_build_plan(n, data, index[n]);
+    const PlanEntry *di;
+    const uint16_t *dd;
+    int rc;
+    if ((rc = upload(e, e->plan_index, index.data(), index.size(), &di))) return rc;
+    if ((rc = upload(e, e->plan_data, data.data(), data.size(), &dd))) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    e->plan_nmax = want;
+    return WFL_OK;
+}
+
 int check_batch(wfl_engine *e, const wfl_batch *in) {
     if (!in || in->n_contigs < 0 || in->n_hits < 0 || in->n_loci < 0) {
         set_err(e, "bad batch sizes");
@@ -120,11 +185,6 @@ int check_batch(wfl_engine *e, const wfl_batch *in) {
     for (int64_t c = 0; c < in->n_contigs; ++c)
         if (in->hit_off[c + 1] < in->hit_off[c] || in->locus_off[c + 1] < in->locus_off[c]) {
             set_err(e, "CSR offsets are not monotone at contig %lld", (long long)c);
-            return WFL_ERR_ARG;
-        }
-    for (int64_t h = 0; h < in->n_hits; ++h)
-        if ((uint32_t)in->hit_taxon[h] >= (uint32_t)e->tax.n_nodes) {
-            set_err(e, "hit %lld: taxon index %d outside the taxonomy", (long long)h, in->hit_taxon[h]);
             return WFL_ERR_ARG;
         }
     return WFL_OK;
@@ -158,7 +218,9 @@ int alloc_outputs(wfl_engine *e) {
     return rc;
 }
 
-int run_kernels(wfl_engine *e) {
+int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all);
+
+int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
     if (!e->have_params || !e->have_tax || !e->have_batch) {
         set_err(e, "params, taxonomy and batch must be set before running");
         return WFL_ERR_STATE;
@@ -187,11 +249,21 @@ int run_kernels(wfl_engine *e) {
     const int64_t *work_list = nullptr;
     int64_t n_work = e->n;
     std::vector<int64_t> replay;
+    bool restart = false;
     CU(cudaEventRecord(e->ev[1], e->stream));
     for (int attempt = 0;; ++attempt) {
         char *slab;
         if ((rc = outbuf(e, e->slab, (size_t)grid * slab_bytes, &slab))) return rc;
-        CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
+        if (attempt == 0 || restart) {
+            CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
+            restart = false;
+        } else {
+            // replay: keep the member-pool bump pointer and the statistics, reset the work queue
+            hc.next_work = 0;
+            hc.n_overflow = 0;
+            hc.slab_need_max = 0;
+            CU(cudaMemcpyAsync(ctr, &hc, sizeof hc, cudaMemcpyHostToDevice, e->stream));
+        }
         ScoreArgs a{};
         a.b = e->b;
         a.t = e->tax;
@@ -203,8 +275,59 @@ int run_kernels(wfl_engine *e) {
         a.slab = slab;
         a.slab_bytes = slab_bytes;
         a.smem_bytes = e->smem_bytes;
+        a.plan_nmax = e->plan_nmax;
+        a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
+        a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
         a.dbg_contig = -1;
-        if (n_work > 0) {
+        if (attempt == 0 && src != nullptr && e->n > 0) {
+            // pipelined plugin call: contigs are cut into chunks of ~chunk_bytes of hit data; chunk k+1
+            // crosses PCIe on the copy stream while chunk k is scored on the compute stream
+            const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
+            int64_t c0 = 0;
+            size_t k = 0;
+            while (c0 < e->n) {
+                int64_t c1 = c0 + 1;
+                const int64_t hb = src->hit_off[c0];
+                while (c1 < e->n && (size_t)(src->hit_off[c1 + 1] - hb) * hit_row <= e->chunk_bytes) ++c1;
+                const size_t h0 = (size_t)src->hit_off[c0], h1 = (size_t)src->hit_off[c1];
+                const size_t l0 = (size_t)src->locus_off[c0], l1 = (size_t)src->locus_off[c1];
+                cudaStream_t cs = e->copy_stream;
+#define CP(dst, srcp, lo, hi)                                                                         \
+    if ((hi) > (lo))                                                                                  \
+    CU(cudaMemcpyAsync(const_cast<void *>(static_cast<const void *>((dst) + (lo))), (srcp) + (lo),    \
+                       ((hi) - (lo)) * sizeof(*(srcp)), cudaMemcpyHostToDevice, cs))
+                CP(e->b.hit_qstart, src->hit_qstart, h0, h1);
+                CP(e->b.hit_qend, src->hit_qend, h0, h1);
+                CP(e->b.hit_taxon, src->hit_taxon, h0, h1);
+                CP(e->b.hit_score, src->hit_score, h0, h1);
+                CP(e->b.hit_scov, src->hit_scov, h0, h1);
+                CP(e->b.hit_strand, src->hit_strand, h0, h1);
+                if (e->S > 0) CP(e->b.hit_sysmask, src->hit_sysmask, h0, h1);
+                CP(e->b.locus_start, src->locus_start, l0, l1);
+                CP(e->b.locus_end, src->locus_end, l0, l1);
+                CP(e->b.locus_strand, src->locus_strand, l0, l1);
+#undef CP
+                if (e->chunk_ev.size() <= k) {
+                    cudaEvent_t evn;
+                    CU(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
+                    e->chunk_ev.push_back(evn);
+                }
+                CU(cudaEventRecord(e->chunk_ev[k], cs));
+                CU(cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
+                CU(cudaMemsetAsync(&ctr->next_work, 0, sizeof(unsigned long long), e->stream));
+                a.work_base = c0;
+                a.n_work = c1 - c0;
+                if (e->threads == 32)
+                    launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, a.n_work), e->stream);
+                else
+                    launch_score_kernel(a, (int)std::min<int64_t>(grid, a.n_work), e->threads, e->stream);
+                CU(cudaGetLastError());
+                e->stats.kernel_launches++;
+                c0 = c1;
+                ++k;
+            }
+            CU(cudaEventRecord(e->ev[5], e->copy_stream));   // end of the last H2D chunk
+        } else if (n_work > 0) {
             if (e->threads == 32)
                 launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, n_work), e->stream);
             else
@@ -215,13 +338,11 @@ int run_kernels(wfl_engine *e) {
         if (attempt == 0) CU(cudaEventRecord(e->ev[2], e->stream));
         CU(cudaMemcpyAsync(&hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
-        acc.matched_pairs += hc.matched_pairs;
-        acc.groups += hc.groups;
-        acc.levels += hc.levels;
-        acc.pairs_tested += hc.pairs_tested;
-        acc.pairs_scored += hc.pairs_scored;
-        acc.smem_contigs += hc.smem_contigs;
-        for (int q = 0; q < 12; ++q) acc.phase_cycles[q] += hc.phase_cycles[q];
+        acc = hc;
+        if (hc.n_badinput) {
+            set_err(e, "%llu contig(s) carry a hit taxon index outside the taxonomy", hc.n_badinput);
+            return WFL_ERR_ARG;
+        }
         if (hc.n_runaway) {
             set_err(e, "Runaway taxonomic recursion in %llu contig(s)", hc.n_runaway);
             return WFL_ERR_RUNAWAY;
@@ -237,7 +358,7 @@ int run_kernels(wfl_engine *e) {
             e->o.mem_pool_cap = (int64_t)(nb.cap / sizeof(int32_t));
             work_list = nullptr;
             n_work = e->n;
-            acc = DevCounters{};
+            restart = true;
             e->stats.workspace_retries++;
             continue;
         }
@@ -294,7 +415,7 @@ int run_kernels(wfl_engine *e) {
     return WFL_OK;
 }
 
-int upload_batch(wfl_engine *e, const wfl_batch *in) {
+int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all) {
     if (!e->have_params || !e->have_tax) {
         set_err(e, "set params and taxonomy before uploading a batch");
         return WFL_ERR_STATE;
@@ -311,20 +432,46 @@ int upload_batch(wfl_engine *e, const wfl_batch *in) {
     b.n_hits = e->nh;
     b.n_loci = e->nl;
     const size_t n1 = (size_t)e->n + 1, nh = (size_t)e->nh, nl = (size_t)e->nl;
+    {
+        int maxlen = 0;
+        for (int64_t i = 0; i < in->n_loci; ++i) {
+            int d = in->locus_end[i] - in->locus_start[i];
+            d = (d < 0 ? -d : d) + 1;
+            maxlen = d > maxlen ? d : maxlen;
+        }
+        if ((rc = ensure_plan_table(e, maxlen))) return rc;
+    }
     CU(cudaEventRecord(e->ev[0], e->stream));
     if ((rc = upload(e, e->in[0], in->hit_off, n1, &b.hit_off))) return rc;
     if ((rc = upload(e, e->in[1], in->locus_off, n1, &b.locus_off))) return rc;
-    if ((rc = upload(e, e->in[2], in->hit_qstart, nh, &b.hit_qstart))) return rc;
-    if ((rc = upload(e, e->in[3], in->hit_qend, nh, &b.hit_qend))) return rc;
-    if ((rc = upload(e, e->in[4], in->hit_taxon, nh, &b.hit_taxon))) return rc;
-    if ((rc = upload(e, e->in[5], in->hit_score, nh, &b.hit_score))) return rc;
-    if ((rc = upload(e, e->in[6], in->hit_scov, nh, &b.hit_scov))) return rc;
-    if ((rc = upload(e, e->in[7], in->hit_strand, nh, &b.hit_strand))) return rc;
-    b.hit_sysmask = nullptr;
-    if (e->S > 0 && (rc = upload(e, e->in[8], in->hit_sysmask, nh, &b.hit_sysmask))) return rc;
-    if ((rc = upload(e, e->in[9], in->locus_start, nl, &b.locus_start))) return rc;
-    if ((rc = upload(e, e->in[10], in->locus_end, nl, &b.locus_end))) return rc;
-    if ((rc = upload(e, e->in[11], in->locus_strand, nl, &b.locus_strand))) return rc;
+    if (copy_all) {
+        if ((rc = upload(e, e->in[2], in->hit_qstart, nh, &b.hit_qstart))) return rc;
+        if ((rc = upload(e, e->in[3], in->hit_qend, nh, &b.hit_qend))) return rc;
+        if ((rc = upload(e, e->in[4], in->hit_taxon, nh, &b.hit_taxon))) return rc;
+        if ((rc = upload(e, e->in[5], in->hit_score, nh, &b.hit_score))) return rc;
+        if ((rc = upload(e, e->in[6], in->hit_scov, nh, &b.hit_scov))) return rc;
+        if ((rc = upload(e, e->in[7], in->hit_strand, nh, &b.hit_strand))) return rc;
+        b.hit_sysmask = nullptr;
+        if (e->S > 0 && (rc = upload(e, e->in[8], in->hit_sysmask, nh, &b.hit_sysmask))) return rc;
+        if ((rc = upload(e, e->in[9], in->locus_start, nl, &b.locus_start))) return rc;
+        if ((rc = upload(e, e->in[10], in->locus_end, nl, &b.locus_end))) return rc;
+        if ((rc = upload(e, e->in[11], in->locus_strand, nl, &b.locus_strand))) return rc;
+    } else {
+        // device arrays only; run_kernels copies them chunk by chunk, overlapped with the kernels
+        rc = 0;
+        rc |= outbuf(e, e->in[2], nh, const_cast<int32_t **>(&b.hit_qstart));
+        rc |= outbuf(e, e->in[3], nh, const_cast<int32_t **>(&b.hit_qend));
+        rc |= outbuf(e, e->in[4], nh, const_cast<int32_t **>(&b.hit_taxon));
+        rc |= outbuf(e, e->in[5], nh, const_cast<double **>(&b.hit_score));
+        rc |= outbuf(e, e->in[6], nh, const_cast<double **>(&b.hit_scov));
+        rc |= outbuf(e, e->in[7], nh, const_cast<int8_t **>(&b.hit_strand));
+        b.hit_sysmask = nullptr;
+        if (e->S > 0) rc |= outbuf(e, e->in[8], nh, const_cast<uint32_t **>(&b.hit_sysmask));
+        rc |= outbuf(e, e->in[9], nl, const_cast<int32_t **>(&b.locus_start));
+        rc |= outbuf(e, e->in[10], nl, const_cast<int32_t **>(&b.locus_end));
+        rc |= outbuf(e, e->in[11], nl, const_cast<int8_t **>(&b.locus_strand));
+        if (rc) return WFL_ERR_CUDA;
+    }
     CU(cudaEventRecord(e->ev[1], e->stream));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaEventElapsedTime(&e->stats.ms_h2d, e->ev[0], e->ev[1]));
@@ -374,9 +521,9 @@ int download(wfl_engine *e, wfl_results *out) {
     rc |= d2h(e, out->call_counts, static_cast<const int64_t *>(e->cm[2].p), 3);
     rc |= d2h(e, out->call_index, static_cast<const int64_t *>(e->cm[3].p), n);
     if (rc) return WFL_ERR_CUDA;
-    CU(cudaEventRecord(e->ev[5], e->stream));
+    CU(cudaEventRecord(e->ev[6], e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    CU(cudaEventElapsedTime(&e->stats.ms_d2h, e->ev[4], e->ev[5]));
+    CU(cudaEventElapsedTime(&e->stats.ms_d2h, e->ev[4], e->ev[6]));
     e->stats.ms_h2d = h2d;
     return WFL_OK;
 }
@@ -406,7 +553,8 @@ int wfl_create(int device, wfl_engine **out) {
     e->device = device;
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return WFL_ERR_CUDA;
     }
@@ -430,8 +578,10 @@ void wfl_destroy(wfl_engine *e) {
     for (auto &b : e->out) fr(b);
     for (auto &b : e->cm) fr(b);
     for (auto &b : e->dbg) fr(b);
-    fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch);
+    fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->chunk_ev) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -502,7 +652,7 @@ int wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent, cons
 int wfl_upload_batch(wfl_engine *e, const wfl_batch *in) {
     if (!e) return WFL_ERR_ARG;
     CU(cudaSetDevice(e->device));
-    return upload_batch(e, in);
+    return stage_inputs(e, in, true);
 }
 
 int wfl_run_resident(wfl_engine *e) {
@@ -523,11 +673,11 @@ int wfl_download_results(wfl_engine *e, wfl_results *out) {
 int wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out) {
     if (!e) return WFL_ERR_ARG;
     CU(cudaSetDevice(e->device));
-    int rc = upload_batch(e, in);
+    int rc = stage_inputs(e, in, false);
     if (rc) return rc;
-    float h2d = e->stats.ms_h2d;
-    if ((rc = run_kernels(e))) return rc;
-    e->stats.ms_h2d = h2d;
+    if ((rc = run_kernels(e, in))) return rc;
+    float h2d = 0.f;
+    if (e->n > 0 && cudaEventElapsedTime(&h2d, e->ev[0], e->ev[5]) == cudaSuccess) e->stats.ms_h2d = h2d;
     return download(e, out);
 }
 
@@ -581,6 +731,8 @@ int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int
     ScoreArgs a{};
     a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
     a.work_list = wl; a.n_work = 1; a.slab = slab; a.slab_bytes = slab_bytes; a.smem_bytes = e->smem_bytes;
+    a.plan_nmax = e->plan_nmax; a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
+    a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
     a.dbg_contig = contig; a.dbg_clade = dc; a.dbg_locus = dl; a.dbg_score = ds; a.dbg_cap = capacity; a.dbg_count = dn;
     if (e->threads == 32)
         launch_score_kernel_warp(a, 1, e->stream);

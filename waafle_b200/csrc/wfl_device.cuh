@@ -43,7 +43,7 @@ struct DevOut {
     int64_t *mem_pos;
     int32_t *mem_pool;
     int64_t mem_pool_cap;
-    uint8_t *status;          // per contig: 0 ok, 1 workspace overflow (replay), 2 runaway
+    uint8_t *status;          // per contig: 0 ok, 1 workspace overflow (replay), 2 runaway, 3 bad input
 };
 
 // Global counters (one struct in device memory, zeroed before each run).
@@ -53,6 +53,7 @@ struct DevCounters {
     unsigned long long slab_need_max;   // max workspace bytes any contig asked for
     unsigned long long n_overflow;      // contigs that overflowed their workspace
     unsigned long long n_runaway;
+    unsigned long long n_badinput;      // contigs with a taxon index outside the taxonomy
     unsigned long long matched_pairs, groups, levels, pairs_tested, pairs_scored, smem_contigs;
     unsigned long long phase_cycles[12];   // thread-0 clock64 deltas per phase (profiling aid)
 };
@@ -64,6 +65,13 @@ struct DevParams {
     int amb_sel, sis_sel;     // which of the three per-clade masks (0:k1 1:k2 2:eps) to use
 };
 
+// Leaf plan of numpy's pairwise sum over n elements: data[off .. off+nleaf) holds
+// (leaf size m) | (number of pending left sums to add after the leaf) << 8; k8 packs up to four
+// distinct m/8 values (ascending, 0 = unused / memo disabled).
+struct PlanEntry {
+    uint32_t off, nleaf, k8;
+};
+
 struct ScoreArgs {
     DevBatch b;
     DevTax t;
@@ -72,9 +80,14 @@ struct ScoreArgs {
     DevCounters *ctr;
     const int64_t *work_list;   // optional list of contig indices (replays); null = 0..n-1
     int64_t n_work;
+    int64_t work_base;          // first contig of this launch when work_list is null
     char *slab;                 // per-CTA global workspace, slab_bytes each
     size_t slab_bytes;
     int smem_bytes;             // dynamic shared memory per CTA
+    // pairwise-sum leaf plans for every gene length 1..plan_nmax (host-built, L2-resident)
+    int plan_nmax;
+    const PlanEntry *plan_index;   // [plan_nmax + 1]
+    const uint16_t *plan_data;
     // test hook: dump the level-0 gene scores of one contig as COO triples
     long long dbg_contig;       // -1 = off
     int32_t *dbg_clade, *dbg_locus;

@@ -491,7 +491,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
         __syncthreads();
         if (tid == 0) {
             unsigned long long w = atomicAdd(&a.ctr->next_work, 1ull);
-            sh.c = (long long)w < a.n_work ? (a.work_list ? a.work_list[w] : (long long)w) : -1;
+            sh.c = (long long)w < a.n_work ? (a.work_list ? a.work_list[w] : a.work_base + (long long)w) : -1;
         }
         __syncthreads();
         const long long c = sh.c;
@@ -602,6 +602,7 @@ __global__ void wfl_score_contigs(const ScoreArgs a) {
                         if (!(ov >= P.p.min_overlap)) continue;
                         if (cl < 0) {
                             cl = a.b.hit_taxon[h0 + h];
+                            if ((u32)cl >= (u32)tax.n_nodes) { cl = tax.root; atomicAdd(&a.ctr->n_badinput, 1ull); }
                             for (int j = 0; j < P.p.jump_taxonomy; ++j) cl = tax.parent[cl];
                             sc = a.b.hit_score[h0 + h];
                         }

@@ -126,10 +126,10 @@ __device__ __noinline__ int warp_lca(const DevTax &t, int v) {
     return v;
 }
 
-// Stable warp multisplit of `n` items by bin (bin_of(i) in [0, nbins)): out[] receives the item
-// indices grouped by bin, original order kept inside each bin.  `cur` is an nbins+1 scratch array;
+// Stable warp multisplit of the item sequence src[0..n) (identity if src == nullptr) by bin key[item]
+// in [0, nbins): out[] receives the items grouped by bin, sequence order kept inside each bin.  `cur` is an nbins+1 scratch array;
 // on return cur[b] = end of bin b (== start of bin b+1).
-__device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, int *cur, int *out) {
+__device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, const int *src, int *cur, int *out) {
     const int lane = lane_id();
 #pragma unroll 1
     for (int b = lane; b <= nbins; b += 32) cur[b] = 0;
@@ -137,7 +137,7 @@ __device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, i
 #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + lane;
-        int b = i < n ? key[i] : nbins;
+        int b = i < n ? key[src ? src[i] : i] : nbins;
         u32 peers = __match_any_sync(FULL, b);
         if ((peers & lt_mask()) == 0) cur[b] += __popc(peers);
         __syncwarp();
@@ -154,9 +154,10 @@ __device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, i
 #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int i = base + lane;
-        int b = i < n ? key[i] : nbins;
+        int it = i < n ? (src ? src[i] : i) : 0;
+        int b = i < n ? key[it] : nbins;
         u32 peers = __match_any_sync(FULL, b);
-        if (i < n) out[cur[b] + __popc(peers & lt_mask())] = i;
+        if (i < n) out[cur[b] + __popc(peers & lt_mask())] = it;
         __syncwarp();
         if (i < n && (peers & lt_mask()) == 0) cur[b] += __popc(peers);
         __syncwarp();
@@ -171,7 +172,10 @@ __device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, i
 // The split tree depends only on n, so it is flattened once per locus into a leaf plan shared by
 // all clades: plan entry = leaf size m | (#pending left sums to add after this leaf) << 8.
 
-// Emit (or just count, if plan == nullptr) the leaf plan of an n-element sum.
+// Emit the leaf plan of an n-element sum (at most plan_cap(n) entries).  Every leaf of a split
+// node has more than 56 elements, hence the bound.
+__device__ __forceinline__ int plan_cap(int n) { return n / 57 + 2; }
+
 __device__ __noinline__ int build_plan(int n, u16 *plan, u8 *k8set) {
     int sz[MAXDEPTH], ch[MAXDEPTH], sp = 0, cnt = 0, nset = 0;
     sz[0] = n;
@@ -238,7 +242,7 @@ struct Site {
             if (a <= pos && pos < b) {
                 v = fmax(v, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
                 nx = min(nx, b);
-                if (sorted) break;
+                if (sorted) break;   // descending score order: the first cover is the max
             } else if (a > pos) {
                 nx = min(nx, a);
             }
@@ -394,12 +398,18 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
 }
 
 // np.mean of the group's site array (waafle_orgscorer.py:403) without materialising it.
-__device__ __noinline__ double group_mean(Site &s, const u16 *plan, int nleaf) {
-    double st[MAXDEPTH];
-    int sp = 0;
+// ord[rs..re) are the group's records (in descending score order if `sorted`).
+__device__ __noinline__ double group_mean(const int *ord, const int *ra, const int *rb, const double *rv, int rs,
+                                          int re, int n, bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
+    Site s;
+    s.ord = ord; s.ra = ra; s.rb = rb; s.rv = rv;
+    s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
+    s.k8[0] = (u8)k8pack; s.k8[1] = (u8)(k8pack >> 8); s.k8[2] = (u8)(k8pack >> 16); s.k8[3] = (u8)(k8pack >> 24);
     s.pos = 0;
     s.run_end = 0;
     s.memo_ok = false;
+    double st[MAXDEPTH];
+    int sp = 0;
 #pragma unroll 1
     for (int l = 0; l < nleaf; ++l) {
         const int e = plan[l], m = e & 0xff, nadd = e >> 8;
@@ -409,7 +419,7 @@ __device__ __noinline__ double group_mean(Site &s, const u16 *plan, int nleaf) {
         for (int q = 0; q < nadd; ++q) val = st[--sp] + val;
         st[sp++] = val;
     }
-    return st[0] / (double)s.n;
+    return st[0] / (double)n;
 }
 
 // Generic sequential pairwise sum for the short gene-level vectors of Contig.score.
@@ -516,17 +526,18 @@ struct Level {   // per-level views shared by the search routines (all pointers 
     const int *l_len;
 };
 
-__device__ __noinline__ void score_clades(const Level &L, int t1, int t2, double &crit, double &rank) {
+__device__ __noinline__ double score_clades(const Level *L, int t1, int t2, double *crit_out) {
     ScoreSrc s;
-    s.r1 = RowCursor{L.g_loc, L.g_score, L.cl_go[t1], L.cl_go[t1 + 1]};
+    s.r1 = RowCursor{L->g_loc, L->g_score, L->cl_go[t1], L->cl_go[t1 + 1]};
     s.two = t2 >= 0;
-    s.r2 = s.two ? RowCursor{L.g_loc, L.g_score, L.cl_go[t2], L.cl_go[t2 + 1]} : s.r1;
-    s.ign = L.ign;
+    s.r2 = s.two ? RowCursor{L->g_loc, L->g_score, L->cl_go[t2], L->cl_go[t2 + 1]} : s.r1;
+    s.ign = L->ign;
     s.i = 0;
     s.crit = __longlong_as_double(0x7ff0000000000000ll);
-    double sum = pairwise_seq(s, L.n_unmasked);
-    crit = s.crit;
-    rank = sum / (double)L.n_unmasked;   // np.mean = add.reduce / n
+    const int n = L->n_unmasked;
+    double sum = pairwise_seq(s, n);
+    *crit_out = s.crit;
+    return sum / (double)n;   // np.mean = add.reduce / n
 }
 
 // Letters of a two-clade option on word w (waafle_orgscorer.py:524-534), before the A/B swap.
@@ -644,10 +655,10 @@ __device__ __noinline__ void pair_decode(long long p, int n, int &i, int &j) {
     j = (int)(p - ii * (2LL * n - ii - 1) / 2) + i + 1;
 }
 
-// hit x locus test: scov / strand / calc_overlap >= --min-overlap (waafle_orgscorer.py:362-367)
-__device__ __noinline__ bool hit_matches(const DevParams &P, bool hit_ok, int hmin, int hmax, signed char hs,
-                                            int lmin, int llen, signed char ls) {
-    if (!hit_ok) return false;
+// hit x locus test after the scov filter: strand / calc_overlap >= --min-overlap
+// (waafle_orgscorer.py:365-367, utils.py:487-500)
+__device__ __noinline__ bool hit_matches(const DevParams &P, int hmin, int hmax, signed char hs, int lmin, int llen,
+                                         signed char ls) {
     if (P.p.stranded && hs != ls) return false;
     int lmax = lmin + llen - 1;
     double ov = 0.0;   // utils.py:492-499
@@ -675,7 +686,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
         long long c = -1;
         if (lane == 0) {
             unsigned long long w = atomicAdd(&a.ctr->next_work, 1ull);
-            c = (long long)w < a.n_work ? (a.work_list ? a.work_list[w] : (long long)w) : -1;
+            c = (long long)w < a.n_work ? (a.work_list ? a.work_list[w] : a.work_base + (long long)w) : -1;
         }
         c = __shfl_sync(FULL, c, 0);
         if (c < 0) break;
@@ -693,9 +704,10 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
         // ---- loci: --min-gene-length filter, GFF order kept (waafle_orgscorer.py:348-352) ----
         int *l_lo = ar.get<int>(Graw), *l_len = ar.get<int>(Graw), *l_raw = ar.get<int>(Graw);
         int *l_base = ar.get<int>(Graw + 2);   // record range of each locus (locus-major records)
-        int *l_poff = ar.get<int>(Graw + 1);   // leaf-plan range of each locus
+        const u16 **l_plan = ar.get<const u16 *>(Graw + 1);   // leaf plan of each locus
+        int *l_nleaf = ar.get<int>(Graw + 1);                 // leaves in it (fallback offset meanwhile)
         signed char *l_str = ar.get<signed char>(Graw);
-        u8 *l_k8 = ar.get<u8>(4 * (size_t)Graw);
+        u32 *l_k8 = ar.get<u32>(Graw + 1);                     // packed m/8 values for the S_k memo
         bool overflow = !ar.ok;
         int G = 0;
 #pragma unroll 1
@@ -728,22 +740,23 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
             r_na = 0, r_nb = 0, r_status = 0;
         long long r_mem = 0;
         double r_crit = 0.0, r_rank = 0.0;
+        bool bad_input = false;
 
         if (!overflow && H > 0 && G > 0) {
-            // ---- K1 pass 1: matches per locus (ballot counts) + leaf-plan sizes ------------------
+            // ---- leaf plans: host-built table for lengths <= plan_nmax, in-kernel build beyond -------
 #pragma unroll 1
             for (int i = lane; i <= G + 1; i += 32) l_base[i] = 0;
             int np_tot = 0;
 #pragma unroll 1
             for (int base = 0; base < G; base += 32) {
-                int i = base + lane, np = 0;
-                if (i < G) np = build_plan(l_len[i], nullptr, nullptr);
-                int tot, ex = warp_excl_scan(np, tot);
-                if (i < G) l_poff[i] = np_tot + ex;
+                int i = base + lane, np = (i < G && l_len[i] > a.plan_nmax) ? plan_cap(l_len[i]) : 0, tot;
+                int ex = warp_excl_scan(np, tot);
+                if (i < G) l_nleaf[i] = np_tot + ex;
                 np_tot += tot;
             }
-            if (lane == 0) l_poff[G] = np_tot;
             __syncwarp();
+            // ---- K1 pass 1: matches per locus (ballot counts) --------------------------------------
+            const bool all_match = P.p.min_overlap <= 0.0;   // disjoint pairs "overlap" 0 >= min_overlap
 #pragma unroll 1
             for (int base = 0; base < H; base += 32) {
                 int h = base + lane;
@@ -760,7 +773,10 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                 if (!__any_sync(FULL, hok)) continue;
 #pragma unroll 1
                 for (int i = 0; i < G; ++i) {
-                    u32 m = __ballot_sync(FULL, hit_matches(P, hok, hmin, hmax, hs, l_lo[i], l_len[i], l_str[i]));
+                    const int lmin = l_lo[i], llen = l_len[i];
+                    bool cand = hok && (all_match || !(lmin > hmax || hmin > lmin + llen - 1));
+                    if (!__any_sync(FULL, cand)) continue;
+                    u32 m = __ballot_sync(FULL, cand && hit_matches(P, hmin, hmax, hs, lmin, llen, l_str[i]));
                     if (lane == 0 && m) l_base[i + 1] += __popc(m);
                 }
             }
@@ -776,16 +792,17 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
             }
             __syncwarp();
             // worst case for this contig (groups <= M + G, clades <= groups + 1): one replay suffices
-            need_hint = 96ull * Graw + 2ull * np_tot + 40ull * (unsigned long long)M +
+            need_hint = 96ull * Graw + 2ull * np_tot + 48ull * (unsigned long long)M +
                         48ull * ((unsigned long long)M + G + 2) +
                         (80ull + 24ull * W) * ((unsigned long long)M + G + 2) + 16ull * (2 * M + 64) +
                         (unsigned long long)G * (64 + 16 * S) + (1ull << 12);
 
             // ---- record arrays (locus-major) ------------------------------------------------------
-            u16 *plan = ar.get<u16>(np_tot);
+            u16 *plan_fb = ar.get<u16>(np_tot);
             double *r_v = ar.get<double>(M);
             int *r_a = ar.get<int>(M), *r_b = ar.get<int>(M), *r_t = ar.get<int>(M), *r_loc = ar.get<int>(M),
                 *r_hit = S > 0 ? ar.get<int>(M) : nullptr;
+            int *base_ord = ar.get<int>(M);   // records in (locus, score descending) order
             double *maxv = ar.get<double>(G);
             u64 *maxb = ar.get<u64>(G);
             u8 *ign = ar.get<u8>(G + 1);
@@ -795,7 +812,19 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
             overflow = !ar.ok;
             if (!overflow) {
 #pragma unroll 1
-                for (int i = lane; i < G; i += 32) build_plan(l_len[i], plan + l_poff[i], l_k8 + 4 * i);
+                for (int i = lane; i < G; i += 32) {
+                    const int len = l_len[i];
+                    if (len <= a.plan_nmax) {
+                        const PlanEntry pe = a.plan_index[len];
+                        l_plan[i] = a.plan_data + pe.off;
+                        l_nleaf[i] = (int)pe.nleaf;
+                        l_k8[i] = pe.k8;
+                    } else {
+                        u16 *dst = plan_fb + l_nleaf[i];
+                        l_plan[i] = dst;
+                        l_nleaf[i] = build_plan(len, dst, reinterpret_cast<u8 *>(&l_k8[i]));
+                    }
+                }
 #pragma unroll 1
                 for (int i = lane; i < G * S; i += 32) { annb[i] = 0; annw[i] = -1; }
                 __syncwarp();
@@ -818,6 +847,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     if (!__any_sync(FULL, hok)) continue;
                     if (hok) {
                         cl = a.b.hit_taxon[h0 + h];
+                        if ((u32)cl >= (u32)tax.n_nodes) { cl = tax.root; bad_input = true; }
 #pragma unroll 1
                         for (int j = 0; j < P.p.jump_taxonomy; ++j) cl = tax.parent[cl];
                         sc = a.b.hit_score[h0 + h];
@@ -826,7 +856,9 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
 #pragma unroll 1
                     for (int i = 0; i < G; ++i) {
                         const int lmin = l_lo[i], len = l_len[i];
-                        bool mt = hit_matches(P, hok, hmin, hmax, hs, lmin, len, l_str[i]);
+                        bool cand = hok && (all_match || !(lmin > hmax || hmin > lmin + len - 1));
+                        if (!__any_sync(FULL, cand)) continue;
+                        bool mt = cand && hit_matches(P, hmin, hmax, hs, lmin, len, l_str[i]);
                         u32 m = __ballot_sync(FULL, mt);
                         if (!m) continue;
                         int cur = l_base[i + 1];
@@ -886,6 +918,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         a.o.ann_winner[(l0 + l_raw[i / S]) * S + (i % S)] = w >= 0 ? (int)(h0 + w) : -1;
                     }
                 }
+                bool have_base_ord = false;
                 PH(0);
 
                 // ---- distinct clades of the contig: hash-dedupe + rank by counting ----------------
@@ -930,10 +963,13 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         }
                         __syncwarp();
 #pragma unroll 1
-                        for (int j = lane; j < T; j += 32) {   // rank = #distinct keys below
-                            int key = hk[dl[j]], rk = 0;
+                        for (int j = lane; j < T; j += 32) map_t[j] = hk[dl[j]];   // compact key list
+                        __syncwarp();
 #pragma unroll 1
-                            for (int q = 0; q < T; ++q) rk += hk[dl[q]] < key;
+                        for (int j = lane; j < T; j += 32) {   // rank = #distinct keys below
+                            int key = map_t[j], rk = 0;
+#pragma unroll 1
+                            for (int q = 0; q < T; ++q) rk += map_t[q] < key;
                             hv[dl[j]] = rk;
                             cl_id[rk] = key;
                         }
@@ -953,10 +989,31 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     ar.smem_used = mark_smem;
                     ar.slab_used = mark_slab;
                     ++n_levels;
+                    if (!have_base_ord) {
+                        // ---- level-invariant base order (built once):
+                        // inside each locus, records by descending score
+                        // (rank by counting; ties keep emission order).  Every later regrouping is a STABLE
+                        // split of this sequence, so each (clade, locus) group arrives score-descending and
+                        // the envelope scan can stop at the first record covering a site.
+#pragma unroll 1
+                        for (int r = lane; r < M; r += 32) {
+                            const int loc = r_loc[r], s0 = l_base[loc], s1 = l_base[loc + 1];
+                            const double v = r_v[r];
+                            int rk = 0;
+#pragma unroll 1
+                            for (int q = s0; q < s1; ++q) {
+                                double vq = r_v[q];
+                                rk += (vq > v) || (vq == v && q < r);
+                            }
+                            base_ord[s0 + rk] = r;
+                        }
+                        __syncwarp();
+                        have_base_ord = true;
+                    }
                     // ---- regroup: stable multisplit of the locus-major records by clade rank ------
                     int *cur = ar.get<int>(T + 2);
                     if (!ar.ok) { overflow = true; break; }
-                    warp_multisplit(M, T, r_t, cur, ord);
+                    warp_multisplit(M, T, r_t, have_base_ord ? base_ord : nullptr, cur, ord);
                     __syncwarp();
                     // groups = maximal runs of equal (clade rank, locus) in ord
                     int t_unk = -1;
@@ -988,7 +1045,8 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     const int Ngrp = spike ? ng - nu + G : ng;
                     n_groups += Ngrp;
                     double *g_score = ar.get<double>(Ngrp);
-                    int *g_rs = ar.get<int>(Ngrp + 1), *g_loc = ar.get<int>(Ngrp), *g_t = ar.get<int>(Ngrp),
+                    int *g_rs = ar.get<int>(Ngrp + 1), *g_re = ar.get<int>(Ngrp + 1), *g_loc = ar.get<int>(Ngrp),
+                        *g_t = ar.get<int>(Ngrp), *gs = ar.get<int>(ng + 1),
                         *g_perm = ar.get<int>(Ngrp), *gcur = ar.get<int>(G + 2);
                     if (!ar.ok) { overflow = true; break; }
                     int gbase = 0;
@@ -1007,14 +1065,21 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         if (f) {
                             int gid = gbase + __popc(m & lt_mask()), dst = gid;
                             if (spike) dst = t < t_unk ? gid : (t == t_unk ? -1 : gid - nu + G);
+                            gs[gid] = r;
                             if (dst >= 0) {
                                 g_rs[dst] = r;
+                                g_re[dst] = gid;   // patched to the end position below
                                 g_loc[dst] = loc;
                                 g_t[dst] = t;
                             }
                         }
                         gbase += __popc(m);
                     }
+                    if (lane == 0) gs[ng] = M;
+                    __syncwarp();
+#pragma unroll 1
+                    for (int g = lane; g < Ngrp; g += 32)
+                        if (!(spike && g >= nlt && g < nlt + G)) g_re[g] = gs[g_re[g] + 1];
                     if (spike)
                         for (int i = lane; i < G; i += 32) {
                             g_rs[nlt + i] = -1;
@@ -1027,7 +1092,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     PH(2);
                     // ---- K2: envelope integral per group, numpy-pairwise-exact ----------------------
                     // groups are visited locus-major so that the lanes of a warp walk the same leaf plan
-                    warp_multisplit(Ngrp, G, g_loc, gcur, g_perm);
+                    warp_multisplit(Ngrp, G, g_loc, nullptr, gcur, g_perm);
                     __syncwarp();
 #pragma unroll 1
                     for (int base = 0; base < Ngrp; base += 32) {
@@ -1037,30 +1102,9 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                             int rs = g_rs[g];
                             if (rs >= 0) {
                                 const int t = g_t[g], loc = g_loc[g];
-                                int re = rs + 1;
-                                while (re < M && r_t[ord[re]] == t && r_loc[ord[re]] == loc) ++re;
-                                const int k = re - rs;
-                                bool sorted = false;
-                                if (k > 4) {   // order the group's records by descending score
-#pragma unroll 1
-                                    for (int x = rs + 1; x < re; ++x) {
-                                        int ix = ord[x];
-                                        double vx = r_v[ix];
-                                        int y = x - 1;
-                                        while (y >= rs && r_v[ord[y]] < vx) {
-                                            ord[y + 1] = ord[y];
-                                            --y;
-                                        }
-                                        ord[y + 1] = ix;
-                                    }
-                                    sorted = true;
-                                }
-                                Site s;
-                                s.ord = ord; s.ra = r_a; s.rb = r_b; s.rv = r_v;
-                                s.rs = rs; s.re = re; s.n = l_len[loc]; s.sorted = sorted;
-                                s.k8[0] = l_k8[4 * loc]; s.k8[1] = l_k8[4 * loc + 1];
-                                s.k8[2] = l_k8[4 * loc + 2]; s.k8[3] = l_k8[4 * loc + 3];
-                                double sc = group_mean(s, plan + l_poff[loc], l_poff[loc + 1] - l_poff[loc]);
+                                const int re = g_re[g];
+                                double sc = group_mean(ord, r_a, r_b, r_v, rs, re, l_len[loc], have_base_ord, l_k8[loc],
+                                                       l_plan[loc], l_nleaf[loc]);
                                 g_score[g] = sc;
                                 if (cl_id[t] != tax.unknown)   // waafle_orgscorer.py:409-411
                                     atomicMax(&maxb[loc], dbits(sc));
@@ -1113,6 +1157,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     u64 *mk0 = ar.get<u64>((size_t)T * W), *mk1 = ar.get<u64>((size_t)T * W),
                         *mk2 = ar.get<u64>((size_t)T * W);
                     u64 *bestm = ar.get<u64>(3 * (size_t)W);
+                    Level *Lp = ar.get<Level>(1);
                     if (!ar.ok) { overflow = true; break; }
 #pragma unroll 1
                     for (int g = lane; g < Ngrp; g += 32)
@@ -1146,7 +1191,9 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         }
                     }
                     __syncwarp();
-                    Level L{G, W, T, Ngrp, nun, g_loc, g_score, cl_id, cl_go, {mk0, mk1, mk2}, um, ign, l_len};
+                    if (lane == 0) *Lp = Level{G, W, T, Ngrp, nun, g_loc, g_score, cl_id, cl_go, {mk0, mk1, mk2}, um, ign, l_len};
+                    __syncwarp();
+                    const Level &L = *Lp;
                     PH(4);
 
                     // ---- K6: one-clade search (explain_one, waafle_orgscorer.py:585-597) -----------
@@ -1159,7 +1206,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         cl_opt[t] = pass;
                         if (pass) {
                             double crit, rank;
-                            score_clades(L, t, -1, crit, rank);
+                            rank = score_clades(Lp, t, -1, &crit);
                             cl_rank[t] = rank;
                             cl_crit[t] = crit;
                             u64 b = dbits(rank);
@@ -1214,32 +1261,69 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         __syncwarp();
                         const long long NP = (long long)T2 * (T2 - 1) / 2;
                         n_ptest += NP;
-                        // pass 1: best rank; ties -> last pair in (clade1, clade2) iteration order
+                        // pass 1: mask prefilter over all pairs (crit >= k2 <=> every non-ignored locus is
+                        // covered at k2 by one of the two clades); survivors are compacted in pair order
+                        size_t room = (ar.smem_cap - ar.smem_used) > (ar.slab_cap - ar.slab_used)
+                                          ? (ar.smem_cap - ar.smem_used) : (ar.slab_cap - ar.slab_used);
+                        long long scap = (long long)(room / 16) - 8;
+                        if (scap > NP) scap = NP;
+                        if (scap < 0) scap = 0;
+                        int *s_i = ar.get<int>((size_t)scap), *s_j = ar.get<int>((size_t)scap);
+                        double *s_rank = ar.get<double>((size_t)scap);
+                        if (!ar.ok) { overflow = true; break; }
+                        int nsurv = 0;
+                        {
+                            int pi = 0, po = 0;   // lane's pair: clade cand[pi] with cand[pi + 1 + po]
+                            if (lane < NP) {
+                                int jj;
+                                pair_decode(lane, T2, pi, jj);
+                                po = jj - pi - 1;
+                            }
+#pragma unroll 1
+                            for (long long pb = 0; pb < NP; pb += 32) {
+                                const bool act = pb + lane < NP;
+                                bool pass = false;
+                                if (act) pass = pair_pass(L, cand[pi], cand[pi + 1 + po]);   // crit < k2 fails (:610)
+                                u32 m = __ballot_sync(FULL, pass);
+                                if (pass) {
+                                    long long dst = (long long)nsurv + __popc(m & lt_mask());
+                                    if (dst < scap) { s_i[dst] = pi; s_j[dst] = pi + 1 + po; }
+                                }
+                                nsurv += __popc(m);
+                                if (act) {   // advance the lane's pair by 32 in i-major order
+                                    po += 32;
+                                    while (pi < T2 - 1 && po >= T2 - 1 - pi) { po -= T2 - 1 - pi; ++pi; }
+                                }
+                            }
+                        }
+                        if (nsurv > scap) {   // survivor list does not fit: replay with a slab sized for all pairs
+                            overflow = true;
+                            need_hint += 16ull * (unsigned long long)NP + 4096ull;
+                            break;
+                        }
+                        n_pscore += nsurv;
+                        __syncwarp();
+                        // pass 2: exact crit / rank of the survivors; best rank, ties -> last pair in
+                        // (clade1, clade2) iteration order
                         double my_rank = -1.0;
                         long long my_p = -1;
-                        int nsc = 0;
 #pragma unroll 1
-                        for (long long p = lane; p < NP; p += 32) {
-                            int i, j;
-                            pair_decode(p, T2, i, j);
-                            int t1 = cand[i], t2 = cand[j];
-                            if (!pair_pass(L, t1, t2)) continue;   // crit < k2 (:610)
-                            ++nsc;
-                            double crit, rank;
-                            score_clades(L, t1, t2, crit, rank);
-                            if (my_p < 0 || rank >= my_rank) { my_rank = rank; my_p = p; }
+                        for (int q = lane; q < nsurv; q += 32) {
+                            double crit;
+                            double rank = score_clades(Lp, cand[s_i[q]], cand[s_j[q]], &crit);
+                            s_rank[q] = rank;
+                            if (my_p < 0 || rank >= my_rank) { my_rank = rank; my_p = q; }
                         }
-                        n_pscore += warp_sum(nsc);
                         u64 pb = warp_max_u64(my_p >= 0 ? dbits(my_rank) : 0ull);
                         const long long bp = warp_max_ll((my_p >= 0 && dbits(my_rank) == pb) ? my_p : -1);
+                        __syncwarp();
                         if (bp >= 0) {
                             // meld_two (waafle_orgscorer.py:633-669)
-                            int bi, bj;
-                            pair_decode(bp, T2, bi, bj);
+                            const int bi = s_i[bp], bj = s_j[bp];
                             TwoEval be;
                             eval_two(L, tax, P, cand[bi], cand[bj], be);
                             double bcrit, brank;
-                            score_clades(L, cand[bi], cand[bj], bcrit, brank);
+                            brank = score_clades(Lp, cand[bi], cand[bj], &bcrit);
                             const bool bunk = be.c1 == tax.unknown || be.c2 == tax.unknown;
 #pragma unroll 1
                             for (int w = lane; w < W; w += 32) {
@@ -1252,14 +1336,9 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                             __syncwarp();
                             int nk = 0, nbad = 0, ndiff = 0, la = -1, lb = -1;
 #pragma unroll 1
-                            for (long long p = lane; p < NP; p += 32) {
-                                int i, j;
-                                pair_decode(p, T2, i, j);
-                                int t1 = cand[i], t2 = cand[j];
-                                if (!pair_pass(L, t1, t2)) continue;
-                                double crit, rank;
-                                score_clades(L, t1, t2, crit, rank);
-                                if (!(brank - rank <= P.p.range)) continue;   // :636
+                            for (int q = lane; q < nsurv; q += 32) {
+                                if (!(brank - s_rank[q] <= P.p.range)) continue;   // :636
+                                const int t1 = cand[s_i[q]], t2 = cand[s_j[q]];
                                 TwoEval ev;
                                 eval_two(L, tax, P, t1, t2, ev);
                                 ++nk;
@@ -1435,8 +1514,10 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                 atomicAdd(&a.ctr->n_overflow, 1ull);
             }
         }
+        if (__any_sync(FULL, bad_input)) r_status = 3;
         if (lane == 0) {
             if (r_status == 2) atomicAdd(&a.ctr->n_runaway, 1ull);
+            if (r_status == 3) atomicAdd(&a.ctr->n_badinput, 1ull);
             a.o.call[c] = (uint8_t)r_call;
             a.o.direction[c] = (uint8_t)r_dir;
             a.o.lifts[c] = lifts;
