@@ -37,8 +37,8 @@ struct wfl_engine {
     int64_t n = 0, nh = 0, nl = 0;
     int S = 0;
     // knobs
-    int threads = 32, smem_bytes = 14 * 1024, ctas_per_sm = 12;
-    size_t slab_bytes = 128 * 1024;
+    int threads = 32, smem_bytes = 10 * 1024, ctas_per_sm = 12;
+    size_t slab_bytes = 256 * 1024;
     // device buffers (grow-only)
     Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
     int plan_nmax = 0;
