@@ -115,8 +115,11 @@ __device__ __noinline__ int lca2(const DevTax &t, int a, int b) {
     if (a < 0) return b;
     if (b < 0) return a;
     int da = t.depth[a], db = t.depth[b];
+#pragma unroll 1
     while (da > db) { a = t.parent[a]; --da; }
+#pragma unroll 1
     while (db > da) { b = t.parent[b]; --db; }
+#pragma unroll 1
     while (a != b) { a = t.parent[a]; b = t.parent[b]; }
     return a;
 }
@@ -218,6 +221,27 @@ __device__ __noinline__ int build_plan(int n, u16 *plan, u8 *k8set) {
     return cnt;
 }
 
+// Envelope run starting at `pos` for one (clade, locus) group: returns its end, *v its value.
+__device__ __noinline__ int site_advance(const int *ord, const int *ra, const int *rb, const double *rv, int rs,
+                                         int re, int n, bool sorted, int pos, double *vout) {
+    double v = 0.0;   // np.zeros(len(locus)), waafle_orgscorer.py:381
+    int nx = n;
+#pragma unroll 1
+    for (int r = rs; r < re; ++r) {
+        int i = ord[r];
+        int a = ra[i], b = rb[i];
+        if (a <= pos && pos < b) {
+            v = fmax(v, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
+            nx = min(nx, b);
+            if (sorted) break;    // descending score order: the first cover is the max
+        } else if (a > pos) {
+            nx = min(nx, a);
+        }
+    }
+    *vout = v;
+    return nx;
+}
+
 // One (clade, locus) group: envelope of its records streamed as constant runs.
 struct Site {
     const int *ord;       // record indices of the group, ord[rs..re)
@@ -233,22 +257,7 @@ struct Site {
     bool memo_ok;
 
     __device__ __forceinline__ void advance() {
-        double v = 0.0;   // np.zeros(len(locus)), waafle_orgscorer.py:381
-        int nx = n;
-#pragma unroll 1
-        for (int r = rs; r < re; ++r) {
-            int i = ord[r];
-            int a = ra[i], b = rb[i];
-            if (a <= pos && pos < b) {
-                v = fmax(v, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
-                nx = min(nx, b);
-                if (sorted) break;   // descending score order: the first cover is the max
-            } else if (a > pos) {
-                nx = min(nx, a);
-            }
-        }
-        run_v = v;
-        run_end = nx;
+        run_end = site_advance(ord, ra, rb, rv, rs, re, n, sorted, pos, &run_v);
         memo_ok = false;
     }
     __device__ __forceinline__ double next() {
@@ -505,7 +514,7 @@ struct ScoreSrc {
     int i;
     bool two;
     double crit;
-    __device__ __forceinline__ double next() {
+    __device__ __noinline__ double next() {
         while (ign[i]) ++i;
         double v = r1.at(i);
         if (two) v = fmax(v, r2.at(i));
