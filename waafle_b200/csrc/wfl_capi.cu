@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,12 @@ struct wfl_engine {
     // device buffers (grow-only)
     Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
     int plan_nmax = 0;
+    // multi-kernel pipeline state
+    int mode = 2;                       // 0: v1 CTA-per-contig, 1: v2 monolithic warp kernel, 2: pipeline
+    int tax_max_depth = 0;
+    size_t pipe_pool_bytes = size_t(8192) << 20;
+    Buf pipe_pool, pipe_ctg, pipe_lists, pipe_cnt, pipe_wq;
+    std::vector<int64_t> h_hit_off, h_locus_off;
     wfl_stats stats{};
     int64_t members_total = 0;
 };
@@ -220,6 +227,54 @@ int alloc_outputs(wfl_engine *e) {
 
 int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all);
 
+// One sub-batch [c0, c1) through the multi-kernel pipeline (wfl_pipeline.cu).
+int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_t c1) {
+    const int L = std::min(std::max(e->tax_max_depth + 1 - e->P.p.jump_taxonomy, 1), 64);
+    int rc;
+    char *pool;
+    PipeCtg *ctg;
+    int *lists, *cnt;
+    unsigned long long *wq;
+    const size_t n = (size_t)e->n;
+    if ((rc = outbuf(e, e->pipe_pool, std::min<size_t>(e->pipe_pool_bytes, 200 * (size_t)e->nh + 9200 * n + 96 * (size_t)e->nl + (size_t(64) << 20)), &pool))) return rc;
+    if ((rc = outbuf(e, e->pipe_ctg, n, &ctg))) return rc;
+    if ((rc = outbuf(e, e->pipe_lists, 3 * n + 16, &lists))) return rc;
+    if ((rc = outbuf(e, e->pipe_cnt, 2 * 66 + 8, &cnt))) return rc;
+    if ((rc = outbuf(e, e->pipe_wq, 3 * 66 + 8, &wq))) return rc;
+    CU(cudaMemsetAsync(cnt, 0, (2 * 66 + 8) * sizeof(int), e->stream));
+    CU(cudaMemsetAsync(wq, 0, (3 * 66 + 8) * sizeof(unsigned long long), e->stream));
+    PipeArgs pa{};
+    pa.b = sa.b; pa.t = sa.t; pa.o = sa.o; pa.P = sa.P; pa.ctr = sa.ctr;
+    pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool.cap;
+    pa.ctg = ctg;
+    pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data;
+    pa.dbg_contig = -1;
+    int *list[3] = {lists, lists + n, lists + 2 * n};
+    int *cnt_act = cnt, *cnt_two = cnt + 66;
+    const int grid = e->sm_count * pipe_ctas_per_sm();
+    pa.wq = wq + 1;
+    pa.work_base = c0; pa.n_work = c1 - c0;
+    pa.list_act = list[0]; pa.cnt_act = &cnt_act[0];
+    launch_pipe_prepare(pa, (int)std::min<int64_t>(grid, c1 - c0), e->stream);
+    for (int lvl = 0; lvl < L; ++lvl) {
+        pa.list_act = list[lvl & 1]; pa.cnt_act = &cnt_act[lvl];
+        pa.list_next = list[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
+        pa.list_two = list[2]; pa.cnt_two = &cnt_two[lvl];
+        pa.wq = wq + 2 + 3 * lvl;
+        launch_pipe_scores(pa, grid, e->stream);
+        pa.wq = wq + 3 + 3 * lvl;
+        launch_pipe_one(pa, grid, e->stream);
+        pa.wq = wq + 4 + 3 * lvl;
+        launch_pipe_two(pa, grid, e->stream);
+    }
+    pa.list_act = list[L & 1]; pa.cnt_act = &cnt_act[L];
+    launch_pipe_leftover(pa, e->stream);
+    CU(cudaGetLastError());
+    e->stats.kernel_launches += 2 + 3 * L;
+    return WFL_OK;
+}
+
+
 int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
     if (!e->have_params || !e->have_tax || !e->have_batch) {
         set_err(e, "params, taxonomy and batch must be set before running");
@@ -279,56 +334,72 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
         a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
         a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
         a.dbg_contig = -1;
-        if (attempt == 0 && src != nullptr && e->n > 0) {
-            // pipelined plugin call: contigs are cut into chunks of ~chunk_bytes of hit data; chunk k+1
-            // crosses PCIe on the copy stream while chunk k is scored on the compute stream
+        if (attempt == 0 && e->n > 0 && (src != nullptr || e->mode == 2)) {
+            // The batch is cut into chunks of contigs.  Plugin call (src != nullptr): chunk k+1 crosses
+            // PCIe on the copy stream while chunk k is scored on the compute stream.  Pipeline mode: a
+            // chunk is also the sub-batch whose intermediate state shares the workspace pool.
             const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
+            const int64_t *hoff = e->h_hit_off.data(), *loff = e->h_locus_off.data();
             int64_t c0 = 0;
             size_t k = 0;
             while (c0 < e->n) {
-                int64_t c1 = c0 + 1;
-                const int64_t hb = src->hit_off[c0];
-                while (c1 < e->n && (size_t)(src->hit_off[c1 + 1] - hb) * hit_row <= e->chunk_bytes) ++c1;
-                const size_t h0 = (size_t)src->hit_off[c0], h1 = (size_t)src->hit_off[c1];
-                const size_t l0 = (size_t)src->locus_off[c0], l1 = (size_t)src->locus_off[c1];
-                cudaStream_t cs = e->copy_stream;
+                int64_t c1 = c0;
+                size_t est = 0;
+                for (;;) {
+                    // workspace estimate per contig (records + table + level arrays), see wfl_pipeline.cu
+                    const size_t h = (size_t)(hoff[c1 + 1] - hoff[c1]), g = (size_t)(loff[c1 + 1] - loff[c1]);
+                    est += 190 * h + 96 * g + 9000;
+                    ++c1;
+                    if (c1 >= e->n) break;
+                    if (src != nullptr && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > e->chunk_bytes) break;
+                    if (e->mode == 2 && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
+                }
+                if (src != nullptr) {
+                    const size_t h0 = (size_t)hoff[c0], h1 = (size_t)hoff[c1];
+                    const size_t l0 = (size_t)loff[c0], l1 = (size_t)loff[c1];
+                    cudaStream_t cs = e->copy_stream;
 #define CP(dst, srcp, lo, hi)                                                                         \
     if ((hi) > (lo))                                                                                  \
     CU(cudaMemcpyAsync(const_cast<void *>(static_cast<const void *>((dst) + (lo))), (srcp) + (lo),    \
                        ((hi) - (lo)) * sizeof(*(srcp)), cudaMemcpyHostToDevice, cs))
-                CP(e->b.hit_qstart, src->hit_qstart, h0, h1);
-                CP(e->b.hit_qend, src->hit_qend, h0, h1);
-                CP(e->b.hit_taxon, src->hit_taxon, h0, h1);
-                CP(e->b.hit_score, src->hit_score, h0, h1);
-                CP(e->b.hit_scov, src->hit_scov, h0, h1);
-                CP(e->b.hit_strand, src->hit_strand, h0, h1);
-                if (e->S > 0) CP(e->b.hit_sysmask, src->hit_sysmask, h0, h1);
-                CP(e->b.locus_start, src->locus_start, l0, l1);
-                CP(e->b.locus_end, src->locus_end, l0, l1);
-                CP(e->b.locus_strand, src->locus_strand, l0, l1);
+                    CP(e->b.hit_qstart, src->hit_qstart, h0, h1);
+                    CP(e->b.hit_qend, src->hit_qend, h0, h1);
+                    CP(e->b.hit_taxon, src->hit_taxon, h0, h1);
+                    CP(e->b.hit_score, src->hit_score, h0, h1);
+                    CP(e->b.hit_scov, src->hit_scov, h0, h1);
+                    CP(e->b.hit_strand, src->hit_strand, h0, h1);
+                    if (e->S > 0) CP(e->b.hit_sysmask, src->hit_sysmask, h0, h1);
+                    CP(e->b.locus_start, src->locus_start, l0, l1);
+                    CP(e->b.locus_end, src->locus_end, l0, l1);
+                    CP(e->b.locus_strand, src->locus_strand, l0, l1);
 #undef CP
-                if (e->chunk_ev.size() <= k) {
-                    cudaEvent_t evn;
-                    CU(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
-                    e->chunk_ev.push_back(evn);
+                    if (e->chunk_ev.size() <= k) {
+                        cudaEvent_t evn;
+                        CU(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
+                        e->chunk_ev.push_back(evn);
+                    }
+                    CU(cudaEventRecord(e->chunk_ev[k], cs));
+                    CU(cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
                 }
-                CU(cudaEventRecord(e->chunk_ev[k], cs));
-                CU(cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
-                CU(cudaMemsetAsync(&ctr->next_work, 0, sizeof(unsigned long long), e->stream));
-                a.work_base = c0;
-                a.n_work = c1 - c0;
-                if (e->threads == 32)
-                    launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, a.n_work), e->stream);
-                else
-                    launch_score_kernel(a, (int)std::min<int64_t>(grid, a.n_work), e->threads, e->stream);
-                CU(cudaGetLastError());
-                e->stats.kernel_launches++;
+                if (e->mode == 2) {
+                    if ((rc = launch_pipeline_chunk(e, a, c0, c1))) return rc;
+                } else {
+                    CU(cudaMemsetAsync(&ctr->next_work, 0, sizeof(unsigned long long), e->stream));
+                    a.work_base = c0;
+                    a.n_work = c1 - c0;
+                    if (e->mode == 1)
+                        launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, a.n_work), e->stream);
+                    else
+                        launch_score_kernel(a, (int)std::min<int64_t>(grid, a.n_work), e->threads, e->stream);
+                    CU(cudaGetLastError());
+                    e->stats.kernel_launches++;
+                }
                 c0 = c1;
                 ++k;
             }
-            CU(cudaEventRecord(e->ev[5], e->copy_stream));   // end of the last H2D chunk
+            if (src != nullptr) CU(cudaEventRecord(e->ev[5], e->copy_stream));   // end of the last H2D chunk
         } else if (n_work > 0) {
-            if (e->threads == 32)
+            if (e->mode != 0)
                 launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, n_work), e->stream);
             else
                 launch_score_kernel(a, (int)std::min<int64_t>(grid, n_work), e->threads, e->stream);
@@ -441,6 +512,8 @@ int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all) {
         }
         if ((rc = ensure_plan_table(e, maxlen))) return rc;
     }
+    e->h_hit_off.assign(in->hit_off, in->hit_off + n1);
+    e->h_locus_off.assign(in->locus_off, in->locus_off + n1);
     CU(cudaEventRecord(e->ev[0], e->stream));
     if ((rc = upload(e, e->in[0], in->hit_off, n1, &b.hit_off))) return rc;
     if ((rc = upload(e, e->in[1], in->locus_off, n1, &b.locus_off))) return rc;
@@ -559,6 +632,13 @@ int wfl_create(int device, wfl_engine **out) {
         return WFL_ERR_CUDA;
     }
     e->sm_count = prop.multiProcessorCount;
+    if (const char *k = getenv("WFL_KERNEL")) {
+        std::string m(k);
+        e->mode = m == "v1" ? 0 : m == "v2" ? 1 : 2;
+    }
+    if (e->mode == 0) { e->threads = 128; e->smem_bytes = 36 * 1024; e->ctas_per_sm = 6; }
+    if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
+    if (const char *k = getenv("WFL_CHUNK_MB")) e->chunk_bytes = (size_t)atoll(k) << 20;
     e->smem_optin = prop.sharedMemPerBlockOptin;
     for (auto &ev : e->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) {
@@ -579,6 +659,7 @@ void wfl_destroy(wfl_engine *e) {
     for (auto &b : e->cm) fr(b);
     for (auto &b : e->dbg) fr(b);
     fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data);
+    fr(e->pipe_pool); fr(e->pipe_ctg); fr(e->pipe_lists); fr(e->pipe_cnt); fr(e->pipe_wq);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->chunk_ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -641,6 +722,8 @@ int wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent, cons
     if ((rc = upload(e, e->tx[2], leaf_count, (size_t)n_nodes, &e->tax.leaf_count))) return rc;
     if ((rc = upload(e, e->tx[3], listed, (size_t)n_nodes, &e->tax.listed))) return rc;
     CU(cudaStreamSynchronize(e->stream));
+    e->tax_max_depth = 0;
+    for (int32_t i = 0; i < n_nodes; ++i) e->tax_max_depth = std::max(e->tax_max_depth, (int)depth[i]);
     e->tax.n_nodes = n_nodes;
     e->tax.root = root_idx;
     e->tax.unknown = unknown_idx;
@@ -734,7 +817,7 @@ int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int
     a.plan_nmax = e->plan_nmax; a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
     a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
     a.dbg_contig = contig; a.dbg_clade = dc; a.dbg_locus = dl; a.dbg_score = ds; a.dbg_cap = capacity; a.dbg_count = dn;
-    if (e->threads == 32)
+    if (e->mode != 0)
         launch_score_kernel_warp(a, 1, e->stream);
     else
         launch_score_kernel(a, 1, e->threads, e->stream);

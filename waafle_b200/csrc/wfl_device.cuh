@@ -99,6 +99,50 @@ struct ScoreArgs {
 void launch_score_kernel(const ScoreArgs &a, int grid, int threads, cudaStream_t s);       // v1: CTA per contig
 void launch_score_kernel_warp(const ScoreArgs &a, int grid, cudaStream_t s);             // v2: warp per contig
 
+
+// ---- multi-kernel pipeline (wfl_pipeline.cu) ------------------------------------------------
+enum { PIPE_DONE = 0, PIPE_ACTIVE = 1 };
+
+// Per-contig context carried between the pipeline kernels.
+struct PipeCtg {
+    unsigned long long offA, offB, offC;   // workspace regions in the pool (loci | records+table | level)
+    unsigned int capA, capB, capC;
+    int G, W, M, T, np_tot, lifts, iter;
+    int Ngrp, ng, nlt, nu, t_unk, nun, hasroot;   // written by the scores kernel for the search kernels
+    int state;
+};
+
+struct PipeArgs {
+    DevBatch b;
+    DevTax t;
+    DevOut o;
+    DevParams P;
+    DevCounters *ctr;
+    unsigned long long *wq;        // work-queue head of THIS launch
+    int64_t n_work, work_base;     // prepare: contig range of the sub-batch
+    char *pool;                    // workspace pool of the sub-batch
+    unsigned long long *pool_used;
+    unsigned long long pool_cap;
+    PipeCtg *ctg;                  // [n_contigs]
+    int *list_act, *list_two, *list_next;   // device work lists (contig indices)
+    int *cnt_act, *cnt_two, *cnt_next;
+    int plan_nmax;
+    const PlanEntry *plan_index;
+    const uint16_t *plan_data;
+    long long dbg_contig;
+    int32_t *dbg_clade, *dbg_locus;
+    double *dbg_score;
+    long long dbg_cap;
+    long long *dbg_count;
+};
+
+void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_leftover(const PipeArgs &a, cudaStream_t s);
+int pipe_ctas_per_sm();
+
 // Compaction (K10): CSR of melded members in contig order + contig indices grouped by call.
 struct CompactArgs {
     int64_t n;
