@@ -262,7 +262,7 @@ def main():
     n_total = batch.n_contigs * world
 
     if rank == 0:
-        # roofline of the dominant kernel (wfl_score_contigs): algorithmic bytes per launch
+        # roofline of the scoring pipeline (every wfl_pipe_* launch of one step): algorithmic bytes per step
         # = 29 B/hit + 9 B/locus + 16 B/contig in, 40 B/contig + G(1+4S) B out,
         # plus 29 B/hit again for every extra taxonomy level a contig is evaluated at.
         H = np.diff(batch.hit_off)
@@ -300,7 +300,7 @@ def main():
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "wfl_score_contigs", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "wfl_pipe_prepare+scores+one+two (all launches of one step; scores is ~54% of it)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms": score_ms / args.steps},

@@ -176,3 +176,48 @@ def test_full_size_properties(engine):
         ref = oracle.score_batch(P.as_dict(), tax.tables(), sub.arrays())
         got = engine.score_batch(sub)
         assert not helpers.compare_results(ref, got)
+
+
+@pytest.mark.parametrize("mode", ["v2", "v1"])
+def test_alternate_kernels_stay_bit_exact(mode, monkeypatch):
+    """The monolithic warp kernel (v2: also the replay path for contigs that outgrow the pipeline's
+    workspace) and the first CTA-per-contig kernel (v1) are selectable with WFL_KERNEL and must give
+    the same bytes as the default multi-kernel pipeline."""
+    from waafle_b200 import synth
+    from waafle_b200.engine import Engine
+    data = synth.generate_config("cfg3", n_contigs=300, seed=61, annotations=True)
+    tax = data.taxonomy()
+    batch = data.to_batch(tax)
+    outs = {}
+    for m in ("pipe", mode):
+        monkeypatch.setenv("WFL_KERNEL", m)
+        for flags in ({}, dict(weak_loci="assign-unknown", range=0.3), dict(jump_taxonomy=1)):
+            P = helpers.params_for(flags, 1)
+            eng = Engine(0, P, tax)
+            outs.setdefault(m, []).append(eng.score_batch(batch))
+            eng.close()
+    for a, b in zip(outs["pipe"], outs[mode]):
+        assert not helpers.compare_results(a, b)
+    ref = oracle.score_batch(helpers.params_for({}, 1).as_dict(), tax.tables(), batch.arrays())
+    assert not helpers.compare_results(ref, outs[mode][0])
+
+
+def test_small_workspace_pool_replays(monkeypatch):
+    """A pool too small for a long contig: it is replayed by the monolithic kernel
+    (workspace_retries > 0) and the results do not change (members included)."""
+    from waafle_b200 import synth
+    from waafle_b200.engine import Engine
+    data = synth.generate_config("cfg4", n_contigs=4, seed=62)
+    tax = data.taxonomy()
+    batch = data.to_batch(tax)
+    P = helpers.params_for(dict(sister_penalty="off", range=0.3), 0)
+    eng = Engine(0, P, tax)
+    full = eng.score_batch(batch)
+    assert eng.stats()["workspace_retries"] == 0
+    eng.close()
+    monkeypatch.setenv("WFL_POOL_MB", "0")
+    eng = Engine(0, P, tax)
+    small = eng.score_batch(batch)
+    assert eng.stats()["workspace_retries"] > 0
+    eng.close()
+    assert not helpers.compare_results(full, small)

@@ -10,8 +10,10 @@ from waafle_b200 import synth                     # noqa: E402
 from waafle_b200.engine import Engine             # noqa: E402
 from waafle_b200.params import OrgscorerParams    # noqa: E402
 
-PHASES = ["match+fill", "clade table", "regroup", "gene scores K2", "weak/masks", "one-clade",
-          "two-clade", "lift", "output"]
+# pipeline mode fills slots 0 (prepare), 3 (scores), 5 (one-clade), 6 (two-clade + lift);
+# the monolithic kernels (WFL_KERNEL=v2 / v1) fill all nine
+PHASES = ["prepare/match+fill", "clade table", "regroup", "scores (K2..masks)", "weak/masks", "one-clade",
+          "two-clade(+lift)", "lift", "output"]
 
 
 def main():
@@ -36,7 +38,7 @@ def main():
         batch.n_contigs / st["ms_kernels"] * 1e3))
     print("cycles/contig %.0f" % (tot / batch.n_contigs))
     for name, cyc in zip(PHASES, st["phase_cycles"]):
-        print("  %-15s %6.2f%%  %10.0f cyc/contig" % (name, 100.0 * cyc / tot, cyc / batch.n_contigs))
+        print("  %-20s %6.2f%%  %10.0f cyc/contig" % (name, 100.0 * cyc / tot, cyc / batch.n_contigs))
     print({k: v for k, v in st.items() if k != "phase_cycles"})
     eng.close()
 

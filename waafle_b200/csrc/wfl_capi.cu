@@ -28,7 +28,7 @@ struct wfl_engine {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> chunk_ev;
-    size_t chunk_bytes = size_t(48) << 20;   // H2D chunk size of the pipelined plugin call
+    size_t chunk_bytes = size_t(192) << 20;  // H2D chunk size of the pipelined plugin call
     std::string err;
     bool have_params = false, have_tax = false, have_batch = false, have_results = false;
     DevParams P{};
