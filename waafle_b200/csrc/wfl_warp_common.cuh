@@ -315,6 +315,44 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
         s.pos = p0 + e;
     }
     const int k8 = m >> 3, body = k8 << 3;
+    if (nr == 2 && rend[0] < body) {
+        // The common case: ONE run boundary b inside the leaf body, v0 before it and v1 after it.
+        // With b = 8*c0 + j0, columns j < j0 hold c0+1 copies of v0 then k8-c0-1 copies of v1 and
+        // columns j >= j0 hold c0 copies of v0 then k8-c0 copies of v1: two add chains that share
+        // their v0 prefix.  (One of v0 / v1 is usually 0 -- the flank of a hit -- and adds nothing.)
+        const int b = rend[0], c0 = b >> 3, j0 = b & 7;
+        const double v0 = rval[0], v1 = rval[1];
+        double x, y;   // column sums of the two classes
+        if (c0 == 0) {
+            x = v0;    // one copy of v0 ...
+            y = v1;    // ... or none: the column starts with v1
+            if (v1 != 0.0) {
+#pragma unroll 1
+                for (int i = 1; i < k8; ++i) { x += v1; y += v1; }
+            }
+        } else {
+            y = v0;
+            if (v0 != 0.0) {
+#pragma unroll 1
+                for (int i = 1; i < c0; ++i) y += v0;   // S_c0(v0)
+            }
+            x = y + v0;                                 // S_{c0+1}(v0)
+            if (v1 != 0.0) {
+                const int nx = k8 - c0 - 1;
+#pragma unroll 1
+                for (int i = 0; i < nx; ++i) { x += v1; y += v1; }
+                y += v1;                                // the lower class holds one more v1
+            }
+        }
+        // fold ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) with r_j = (j < j0 ? x : y)
+        const double r0 = 0 < j0 ? x : y, r1 = 1 < j0 ? x : y, r2 = 2 < j0 ? x : y, r3 = 3 < j0 ? x : y;
+        const double r4 = 4 < j0 ? x : y, r5 = 5 < j0 ? x : y, r6 = 6 < j0 ? x : y;
+        double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + y));
+#pragma unroll 1
+        for (int p = body; p < m; ++p) res += v1;   // the n % 8 tail lies behind the boundary
+        s.pos = p0 + m;
+        return res;
+    }
     if (nr > 0) {
         // column j accumulates a[j], a[8+j], ...: runs enter it as (count, value) stretches;
         // neighbouring columns differ only where a run boundary b has b % 8 == j.  The eight
