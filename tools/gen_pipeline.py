@@ -41,7 +41,9 @@ F = F.replace("have_base_ord ? base_ord : nullptr", "base_ord")
 F = F.replace("                    const int Ngrp = spike ? ng - nu + G : ng;\n", "                    Ngrp = spike ? ng - nu + G : ng;\n")
 F = F.replace("                    int t_unk = -1;\n", "                    t_unk = -1;\n")
 F = F.replace("                    int ng = 0, nlt = 0, nu = 0;\n", "                    ng = 0; nlt = 0; nu = 0;\n")
-F = re.sub(r"                    int \*cur = ar\.get<int>\(T \+ 2\);\n", "                    DECL_CUR\n", F)
+F = re.sub(r"                    int \*cur = ar\.get<int>\(T \+ 2\);\n.*?double \*s_v = ar\.get<double>\(M\);\n",
+           "                    DECL_CUR\n", F, flags=re.S)
+assert "DECL_CUR" in F
 F = re.sub(r"                    double \*g_score = ar\.get<double>\(Ngrp\);\n.*?\*gcur = ar\.get<int>\(G \+ 2\);\n",
            "                    DECL_GROUPS\n", F, flags=re.S)
 G2 = cut("                    // ---- K2: envelope integral per group", "                    PH(3);")
@@ -139,7 +141,10 @@ namespace {
     int *map_t = ar.get<int>(M + 2);                                                                \
     u8 *fo = ar.get<u8>(M + 2);
 
-#define DECL_CUR int *cur = al.get<int>(T + 2);
+#define DECL_CUR                                                                                    \
+    int *cur = al.get<int>(T + 2);                                                                  \
+    int *s_a = al.get<int>(M), *s_b = al.get<int>(M);                                               \
+    double *s_v = al.get<double>(M);
 
 #define DECL_GROUPS                                                                                 \
     double *g_score = al.get<double>(Ngrp);                                                         \
@@ -178,7 +183,7 @@ __device__ __forceinline__ size_t record_bytes(int M, int G, int W, int S, int n
 // region C: bound on the per-level arrays once the number of distinct clades T is known
 __device__ __forceinline__ size_t level_bytes(int T, int M, int G, int W) {
     size_t t = (size_t)T, ngb = (size_t)min((long long)M, (long long)T * G) + (size_t)G + 1;
-    return al16(4 * (t + 2)) + 40 * ngb + al16(4 * ((size_t)G + 2)) + 160 + 27 * t + 24 * (size_t)W * t + 24 * (size_t)W +
+    return al16(4 * (t + 2)) + 16 * (size_t)M + 48 + 40 * ngb + al16(4 * ((size_t)G + 2)) + 160 + 27 * t + 24 * (size_t)W * t + 24 * (size_t)W +
            256 + sizeof(Level) + al16(4 * (t + 1)) + 16 * 25 + 6144;
 }
 
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_one(const PipeArgs
         DECL_CUR
         DECL_GROUPS
         DECL_CLADES
-        (void)cur; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
+        (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
         (void)cand; (void)memB; (void)mk1; (void)mk2; (void)bestm; (void)cl_go;
         const Level &L = *Lp;
         (void)L;
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
         DECL_CUR
         DECL_GROUPS
         DECL_CLADES
-        (void)cur; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
+        (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
         (void)cl_rank; (void)cl_crit; (void)cl_opt; (void)mk0; (void)mk2; (void)cl_go;
         const Level &L = *Lp;
         bool overflow = false, lifted = false;

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
             }
             __syncwarp();
             // worst case for this contig (groups <= M + G, clades <= groups + 1): one replay suffices
-            need_hint = 96ull * Graw + 2ull * np_tot + 48ull * (unsigned long long)M +
+            need_hint = 96ull * Graw + 2ull * np_tot + 64ull * (unsigned long long)M +
                         48ull * ((unsigned long long)M + G + 2) +
                         (80ull + 24ull * W) * ((unsigned long long)M + G + 2) + 16ull * (2 * M + 64) +
                         (unsigned long long)G * (64 + 16 * S) + (1ull << 12);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
 #pragma unroll 1
                         for (int j = lane; j < T; j += 32) {   // rank = #distinct keys below
                             int key = map_t[j], rk = 0;
-#pragma unroll 1
+#pragma unroll 4
                             for (int q = 0; q < T; ++q) rk += map_t[q] < key;
                             hv[dl[j]] = rk;
                             cl_id[rk] = key;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                             const int loc = r_loc[r], s0 = l_base[loc], s1 = l_base[loc + 1];
                             const double v = r_v[r];
                             int rk = 0;
-#pragma unroll 1
+#pragma unroll 4
                             for (int q = s0; q < s1; ++q) {
                                 double vq = r_v[q];
                                 rk += (vq > v) || (vq == v && q < r);
@@ -370,9 +370,19 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     }
                     // ---- regroup: stable multisplit of the locus-major records by clade rank ------
                     int *cur = ar.get<int>(T + 2);
+                    int *s_a = ar.get<int>(M), *s_b = ar.get<int>(M);
+                    double *s_v = ar.get<double>(M);
                     if (!ar.ok) { overflow = true; break; }
                     warp_multisplit(M, T, r_t, have_base_ord ? base_ord : nullptr, cur, ord);
                     __syncwarp();
+                    // slices and scores copied into group order: the envelope scans read them contiguously
+#pragma unroll 1
+                    for (int r = lane; r < M; r += 32) {
+                        const int i = ord[r];
+                        s_a[r] = r_a[i];
+                        s_b[r] = r_b[i];
+                        s_v[r] = r_v[i];
+                    }
                     // groups = maximal runs of equal (clade rank, locus) in ord
                     int t_unk = -1;
                     if (spike) {
@@ -461,7 +471,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                             if (rs >= 0) {
                                 const int t = g_t[g], loc = g_loc[g];
                                 const int re = g_re[g];
-                                double sc = group_mean(ord, r_a, r_b, r_v, rs, re, l_len[loc], have_base_ord, l_k8[loc],
+                                double sc = group_mean(s_a, s_b, s_v, rs, re, l_len[loc], have_base_ord, l_k8[loc],
                                                        l_plan[loc], l_nleaf[loc]);
                                 g_score[g] = sc;
                                 if (cl_id[t] != tax.unknown)   // waafle_orgscorer.py:409-411

@@ -199,17 +199,17 @@ __device__ __noinline__ int build_plan(int n, u16 *plan, u8 *k8set) {
     return cnt;
 }
 
-// Envelope run starting at `pos` for one (clade, locus) group: returns its end, *v its value.
-__device__ __noinline__ int site_advance(const int *ord, const int *ra, const int *rb, const double *rv, int rs,
-                                         int re, int n, bool sorted, int pos, double *vout) {
+// Envelope run starting at `pos` for one (clade, locus) group whose records are ra/rb/rv[rs..re)
+// (copies in group order): returns its end, *v its value.
+__device__ __noinline__ int site_advance(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
+                                         bool sorted, int pos, double *vout) {
     double v = 0.0;   // np.zeros(len(locus)), waafle_orgscorer.py:381
     int nx = n;
 #pragma unroll 1
     for (int r = rs; r < re; ++r) {
-        int i = ord[r];
-        int a = ra[i], b = rb[i];
+        int a = ra[r], b = rb[r];
         if (a <= pos && pos < b) {
-            v = fmax(v, rv[i]);   // np.maximum(slice, score), waafle_orgscorer.py:382
+            v = fmax(v, rv[r]);   // np.maximum(slice, score), waafle_orgscorer.py:382
             nx = min(nx, b);
             if (sorted) break;    // descending score order: the first cover is the max
         } else if (a > pos) {
@@ -222,9 +222,8 @@ __device__ __noinline__ int site_advance(const int *ord, const int *ra, const in
 
 // One (clade, locus) group: envelope of its records streamed as constant runs.
 struct Site {
-    const int *ord;       // record indices of the group, ord[rs..re)
-    const int *ra, *rb;   // python-slice [a, b) of each record inside the gene
-    const double *rv;     // waafle_score of each record
+    const int *ra, *rb;   // python-slice [a, b) of the group's records, [rs..re) in group order
+    const double *rv;     // their waafle_scores
     int rs, re, n;
     bool sorted;          // records in descending score order -> first covering record is the max
     int pos, run_end;
@@ -235,7 +234,7 @@ struct Site {
     bool memo_ok;
 
     __device__ __forceinline__ void advance() {
-        run_end = site_advance(ord, ra, rb, rv, rs, re, n, sorted, pos, &run_v);
+        run_end = site_advance(ra, rb, rv, rs, re, n, sorted, pos, &run_v);
         memo_ok = false;
     }
     __device__ __forceinline__ double next() {
@@ -423,11 +422,11 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
 }
 
 // np.mean of the group's site array (waafle_orgscorer.py:403) without materialising it.
-// ord[rs..re) are the group's records (in descending score order if `sorted`).
-__device__ __noinline__ double group_mean(const int *ord, const int *ra, const int *rb, const double *rv, int rs,
-                                          int re, int n, bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
+// ra/rb/rv[rs..re) are the group's records (in descending score order if `sorted`).
+__device__ __noinline__ double group_mean(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
+                                          bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
     Site s;
-    s.ord = ord; s.ra = ra; s.rb = rb; s.rv = rv;
+    s.ra = ra; s.rb = rb; s.rv = rv;
     s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
     s.k8[0] = (u8)k8pack; s.k8[1] = (u8)(k8pack >> 8); s.k8[2] = (u8)(k8pack >> 16); s.k8[3] = (u8)(k8pack >> 24);
     s.pos = 0;
