@@ -33,7 +33,7 @@ B = cut("            // ---- leaf plans: host-built table", "            // ----
 B = B.replace("            int M = 0;\n", "            M = 0;\n").replace("            int np_tot = 0;\n", "            np_tot = 0;\n")
 C = cut("#pragma unroll 1\n                for (int i = lane; i < G; i += 32) {\n                    const int len = l_len[i];",
         "                bool have_base_ord = false;")
-D = cut("                {\n                    int cap = 64;", "                PH(1);")
+D = cut("                const int nwords = (tax.n_nodes + 31) >> 5;", "                PH(1);")
 E = cut("                    if (!have_base_ord) {", "                    // ---- regroup: stable multisplit")
 E = E.replace("                    if (!have_base_ord) {\n", "                    {\n").replace("                        have_base_ord = true;\n", "")
 F = cut("                    // ---- regroup: stable multisplit", "                    PH(2);")
@@ -169,7 +169,7 @@ __device__ __forceinline__ size_t loci_bytes(int Graw) {
            2 * al16(4 * ((size_t)Graw + 1)) + al16((size_t)Graw);
 }
 // region B: DECL_RECORDS exactly, plus the temporary hash table of the clade-table build
-__device__ __forceinline__ size_t record_bytes(int M, int G, int W, int S, int np_tot, size_t *persist) {
+__device__ __forceinline__ size_t record_bytes(int M, int G, int W, int S, int np_tot, int nwords, size_t *persist) {
     size_t m = (size_t)M, g = (size_t)G;
     size_t p = al16(2 * (size_t)np_tot) + al16(8 * m) + 4 * al16(4 * m) + (S > 0 ? al16(4 * m) : 0) + al16(4 * m) +
                2 * al16(8 * g) + al16(g + 1) + al16(8 * (size_t)W) +
@@ -178,7 +178,9 @@ __device__ __forceinline__ size_t record_bytes(int M, int G, int W, int S, int n
     *persist = p;
     size_t cap = 64;
     while (cap < 2 * (m + 1)) cap <<= 1;
-    return p + 2 * al16(4 * cap) + al16(4 * (m + 1)) + 64;
+    size_t hash_tmp = 2 * al16(4 * cap) + al16(4 * (m + 1)) + 64;
+    size_t bitmap_tmp = nwords <= BITMAP_MAX_WORDS ? 2 * al16(4 * ((size_t)nwords + 1)) + 64 : 0;
+    return p + (nwords <= BITMAP_MAX_WORDS ? bitmap_tmp : hash_tmp);
 }
 // region C: bound on the per-level arrays once the number of distinct clades T is known
 __device__ __forceinline__ size_t level_bytes(int T, int M, int G, int W) {
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
 @B@
             // region B
             size_t persist = 0;
-            const size_t capB = record_bytes(M, G, W, S, np_tot, &persist);
+            const size_t capB = record_bytes(M, G, W, S, np_tot, (tax.n_nodes + 31) >> 5, &persist);
             unsigned long long offB = 0;
             if (lane == 0) offB = atomicAdd(a.pool_used, (unsigned long long)((capB + 255) & ~size_t(255)));
             offB = __shfl_sync(FULL, offB, 0);

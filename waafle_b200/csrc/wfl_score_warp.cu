@@ -288,7 +288,48 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                 int *map_t = ar.get<int>(M + 2);
                 u8 *fo = ar.get<u8>(M + 2);
                 const size_t mark_smem = ar.smem_used, mark_slab = ar.slab_used;
-                {
+                const int nwords = (tax.n_nodes + 31) >> 5;
+                if (nwords <= BITMAP_MAX_WORDS) {
+                    // small taxonomies: presence bitmap over the node indices; the rank of a clade among the
+                    // contig's clades is a prefix popcount (ascending node index == ascending name)
+                    u32 *bm = ar.get<u32>(nwords);
+                    int *bpre = ar.get<int>(nwords + 1);
+                    if (!ar.ok) overflow = true;
+                    if (!overflow) {
+#pragma unroll 1
+                        for (int w = lane; w < nwords; w += 32) bm[w] = 0;
+                        __syncwarp();
+#pragma unroll 1
+                        for (int r = lane; r < M + (spike ? 1 : 0); r += 32) {
+                            const int key = r < M ? r_t[r] : tax.unknown;
+                            atomicOr(&bm[key >> 5], 1u << (key & 31));
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int base = 0; base < nwords; base += 32) {
+                            const int w = base + lane;
+                            const u32 bits = w < nwords ? bm[w] : 0u;
+                            int tot, ex = warp_excl_scan(__popc(bits), tot);
+                            if (w < nwords) {
+                                int pos = T + ex;
+                                bpre[w] = pos;
+                                u32 b = bits;
+                                while (b) {
+                                    cl_id[pos++] = (w << 5) + __ffs(b) - 1;
+                                    b &= b - 1;
+                                }
+                            }
+                            T += tot;
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int r = lane; r < M; r += 32) {
+                            const int key = r_t[r];
+                            r_t[r] = bpre[key >> 5] + __popc(bm[key >> 5] & ((1u << (key & 31)) - 1u));
+                        }
+                        __syncwarp();
+                    }
+                } else {
                     int cap = 64;
                     while (cap < 2 * (M + 1)) cap <<= 1;
                     int *hk = ar.get<int>(cap), *hv = ar.get<int>(cap);

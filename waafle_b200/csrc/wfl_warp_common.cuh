@@ -14,6 +14,7 @@ typedef unsigned char u8;
 
 constexpr u32 FULL = 0xffffffffu;
 constexpr int MAXDEPTH = 28;   // pairwise tree depth for n < 2^31
+constexpr int BITMAP_MAX_WORDS = 1024;   // taxonomies up to 32768 nodes use the bitmap clade table
 constexpr int RMAX = 6;        // envelope runs handled per mixed leaf before the per-site fallback
 
 // Order-preserving map double -> u64 (max on the bits == max on the doubles).
