@@ -231,11 +231,10 @@ def main():
     st = eng.stats()
 
     # ---- end-to-end leg: pinned host buffers through the plugin call ----
-    keep, harr = [], {}
-    for k, v in batch.arrays().items():
-        t, hv = pinned_like(np.ascontiguousarray(v))
-        keep.append(t)
-        harr[k] = hv
+    from waafle_b200.engine import PinnedArena
+    pin = PinnedArena()
+    harr = {k: pin.like(np.ascontiguousarray(v)) for k, v in batch.arrays().items()}
+    eng.use_pinned_results(True)
     h2d_bytes = int(sum(v.nbytes for v in harr.values()))
     out = eng.score_batch(harr)
     d2h_bytes = int(sum(np.asarray(v).nbytes for v in out.values()))
@@ -251,6 +250,7 @@ def main():
             dist.all_reduce(cc)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t1)
+    st_e2e = eng.stats()
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -298,7 +298,9 @@ def main():
                        "wall_ms_per_step": wall_ms / args.steps},
             "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "last_call_ms": {"h2d_window": st_e2e["ms_h2d"], "kernels_window": st_e2e["ms_kernels"],
+                                     "d2h": st_e2e["ms_d2h"]}},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "wfl_pipe_prepare+scores+one+two (all launches of one step; scores is ~54% of it)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -313,6 +315,7 @@ def main():
         }
         print(json.dumps(line))
     eng.close()
+    pin.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -19,6 +19,7 @@
 #ifndef WAAFLE_B200_H
 #define WAAFLE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -164,6 +165,11 @@ int  wfl_get_stats(const wfl_engine *e, wfl_stats *out);
 /* Tuning knobs (all optional): threads per CTA, dynamic shared memory bytes per CTA,
  * CTAs per SM.  0 keeps the default. */
 int  wfl_configure(wfl_engine *e, int threads, int smem_bytes, int ctas_per_sm);
+
+/* Page-locked host memory for callers without a CUDA binding of their own (pinned buffers make the
+ * H2D / D2H copies of wfl_score_batch asynchronous and ~2x faster).  Free with wfl_host_free. */
+int  wfl_host_alloc(size_t bytes, void **out);
+void wfl_host_free(void *p);
 
 /* Test hook: level-0 gene scores of one contig of the resident batch as COO triples
  * (clade, retained-locus index, score); returns the number of triples or <0. */

@@ -28,7 +28,7 @@ struct wfl_engine {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> chunk_ev;
-    size_t chunk_bytes = size_t(192) << 20;  // H2D chunk size of the pipelined plugin call
+    size_t chunk_bytes = size_t(128) << 20;  // H2D chunk size of the pipelined plugin call
     std::string err;
     bool have_params = false, have_tax = false, have_batch = false, have_results = false;
     DevParams P{};
@@ -351,7 +351,9 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
                     est += 190 * h + 96 * g + 9000;
                     ++c1;
                     if (c1 >= e->n) break;
-                    if (src != nullptr && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > e->chunk_bytes) break;
+                    // the first chunk is small so that the kernels start early; later ones amortise launches
+                    // the first chunk is small so that the kernels start early; later ones amortise launches
+                    if (src != nullptr && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > (k == 0 ? e->chunk_bytes / 4 : e->chunk_bytes)) break;
                     if (e->mode == 2 && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
                 }
                 if (src != nullptr) {
@@ -762,6 +764,17 @@ int wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out) {
     float h2d = 0.f;
     if (e->n > 0 && cudaEventElapsedTime(&h2d, e->ev[0], e->ev[5]) == cudaSuccess) e->stats.ms_h2d = h2d;
     return download(e, out);
+}
+
+int wfl_host_alloc(size_t bytes, void **out) {
+    if (!out) return WFL_ERR_ARG;
+    *out = nullptr;
+    if (cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) return WFL_ERR_CUDA;
+    return WFL_OK;
+}
+
+void wfl_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int wfl_get_stats(const wfl_engine *e, wfl_stats *out) {

@@ -24,7 +24,7 @@ c_u8p = ctypes.POINTER(ctypes.c_uint8)
 EXPORTS = ["wfl_abi_version", "wfl_device_count", "wfl_create", "wfl_destroy", "wfl_last_error",
            "wfl_set_params", "wfl_set_taxonomy", "wfl_score_batch", "wfl_upload_batch",
            "wfl_run_resident", "wfl_download_results", "wfl_get_stats", "wfl_configure",
-           "wfl_debug_gene_scores"]
+           "wfl_debug_gene_scores", "wfl_host_alloc", "wfl_host_free"]
 
 
 class CBatch(ctypes.Structure):
@@ -93,6 +93,9 @@ def load_library(path=None):
     lib.wfl_debug_gene_scores.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_i32p, c_i32p, c_f64p,
                                           ctypes.c_int64]
     lib.wfl_debug_gene_scores.restype = ctypes.c_int64
+    lib.wfl_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    lib.wfl_host_free.argtypes = [ctypes.c_void_p]
+    lib.wfl_host_free.restype = None
     if path == _LIB_PATH:
         _lib = lib
     return lib
@@ -107,6 +110,34 @@ def _as(a, dtype):
     if a.dtype != dtype or not a.flags.c_contiguous:
         a = np.ascontiguousarray(a, dtype=dtype)
     return a
+
+
+class PinnedArena:
+    """Page-locked host arrays from wfl_host_alloc (freed when the arena is closed)."""
+
+    def __init__(self, lib=None):
+        self._lib = lib or load_library()
+        self._ptrs = []
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        p = ctypes.c_void_p()
+        if self._lib.wfl_host_alloc(max(1, n * dtype.itemsize), ctypes.byref(p)) != 0 or not p:
+            raise EngineError("wfl_host_alloc failed")
+        self._ptrs.append(p)
+        buf = (ctypes.c_uint8 * max(1, n * dtype.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def like(self, a):
+        out = self.empty(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def close(self):
+        for p in self._ptrs:
+            self._lib.wfl_host_free(p)
+        self._ptrs = []
 
 
 class Engine:
@@ -124,13 +155,28 @@ class Engine:
         self._h = h
         self.device = device
         self._keep = {}
+        self._pinned = None
+        self._res_cache = {}
         self.n_systems = 0
         if params is not None:
             self.set_params(params)
         if taxonomy is not None:
             self.set_taxonomy(taxonomy)
 
+    def use_pinned_results(self, on=True):
+        """Keep the result arrays in page-locked memory and reuse them between calls (the arrays a
+        call returns are then overwritten by the next call)."""
+        if on and self._pinned is None:
+            self._pinned = PinnedArena(self._lib)
+        if not on and self._pinned is not None:
+            self._pinned.close()
+            self._pinned = None
+        self._res_cache = {}
+
     def close(self):
+        if getattr(self, "_pinned", None):
+            self._pinned.close()
+            self._pinned = None
         if getattr(self, "_h", None):
             self._lib.wfl_destroy(self._h)
             self._h = None
@@ -191,6 +237,22 @@ class Engine:
 
     def _alloc_results(self, n, nl, members_capacity):
         S = self.n_systems
+        if self._pinned is not None:
+            key = (n, nl, S, max(1, members_capacity))
+            if key not in self._res_cache:
+                e = self._pinned.empty
+                self._res_cache = {key: dict(
+                    call=e(n, np.uint8), direction=e(n, np.uint8), lifts=e(n, np.int32), clade1=e(n, np.int32),
+                    clade2=e(n, np.int32), lca=e(n, np.int32), best1=e(n, np.int32), best2=e(n, np.int32),
+                    crit=e(n, np.float64), rank=e(n, np.float64), member_off=e(n + 1, np.int64),
+                    n_members_a=e(n, np.int32), members=e(max(1, members_capacity), np.int32),
+                    synteny=e(nl, np.uint8), locus_flags=e(nl, np.uint8), ann_winner=e((nl, S), np.int32),
+                    call_counts=e(3, np.int64), call_index=e(n, np.int64))}
+            r = dict(self._res_cache[key])
+            cr = CResults(members_capacity=len(r["members"]), members_used=0)
+            for name, arr in r.items():
+                setattr(cr, name, _ptr(arr, dict(CResults._fields_)[name]._type_))
+            return r, cr
         r = dict(
             call=np.empty(n, np.uint8), direction=np.empty(n, np.uint8),
             lifts=np.empty(n, np.int32), clade1=np.empty(n, np.int32),
