@@ -28,7 +28,7 @@ def dedent(block, n):
 
 
 A = cut("        bool overflow = !ar.ok;\n        int G = 0;", "        const int W = (G + 63) >> 6;")
-A = A.replace("        bool overflow = !ar.ok;\n", "        overflow = !ar.ok;\n")
+A = A.replace("        bool overflow = !ar.ok;\n", "        overflow = !arA.ok;\n")
 B = cut("            // ---- leaf plans: host-built table", "            // ---- record arrays (locus-major)")
 B = B.replace("            int M = 0;\n", "            M = 0;\n").replace("            int np_tot = 0;\n", "            np_tot = 0;\n")
 C = cut("#pragma unroll 1\n                for (int i = lane; i < G; i += 32) {\n                    const int len = l_len[i];",
@@ -44,7 +44,7 @@ F = F.replace("                    int ng = 0, nlt = 0, nu = 0;\n", "           
 F = re.sub(r"                    int \*cur = ar\.get<int>\(T \+ 2\);\n.*?double \*s_v = ar\.get<double>\(M\);\n",
            "                    DECL_CUR\n", F, flags=re.S)
 assert "DECL_CUR" in F
-F = re.sub(r"                    double \*g_score = ar\.get<double>\(Ngrp\);\n.*?\*gcur = ar\.get<int>\(G \+ 2\);\n",
+F = re.sub(r"                    double \*g_score = ar\.get<double>\(Ngrp\);\n.*?\*gcur = ar\.get<int>\(2 \* G \+ 2\);\n",
            "                    DECL_GROUPS\n", F, flags=re.S)
 G2 = cut("                    // ---- K2: envelope integral per group", "                    PH(3);")
 G2 = G2.replace("have_base_ord", "true")
@@ -82,7 +82,14 @@ L2 = L2.replace("""                        int *s_i = al.get<int>((size_t)scap),
                         double *s_rank = ax.get<double>((size_t)scap);
                         if (!ax.ok) { overflow = true; break; }
 """)
-assert "Arena ax = al;" in L2
+L2 = L2.replace("""                        size_t room = (al.smem_cap - al.smem_used) > (al.slab_cap - al.slab_used)
+                                          ? (al.smem_cap - al.smem_used) : (al.slab_cap - al.slab_used);
+""", """                        size_t room = al.cap > al.used ? al.cap - al.used : 0;
+""")
+L2 = L2.replace("Arena ax = al;", "LinArena ax = al;").replace("ax = Arena{a.pool + off, nullptr, (size_t)want, 0, 0, 0, true, true};", "ax = LinArena{a.pool + off, (size_t)want, 0, true};")
+L2 = L2.replace("long long scap = (long long)(room / 16) - 8;",
+                "long long scap = ((long long)room - 4LL * (T + 1) - 256) / 16;   // leave room for the lift's parent table")
+assert "LinArena ax = al;" in L2 and "al.cap - al.used" in L2 and "4LL * (T + 1)" in L2
 Mm = Mm  # members block touches no arena
 
 LEVEL_BLOCKS = dict(F=F, G2=G2, H=H, I=I, J=J, K=K, L2=L2, Mm=Mm, N=N)
@@ -116,13 +123,28 @@ namespace {
 #define WFL_PIPE_CPSM 32   // resident single-warp CTAs per SM the pipeline kernels are compiled for
 #endif
 
+// Linear bump arena over one workspace region: region sizes are exact (loci_bytes / record_bytes) or
+// bounds (level_bytes), so carving is a pointer increment plus one capacity compare.
+struct LinArena {
+    char *base;
+    size_t cap, used;
+    bool ok;
+    template <class T>
+    __device__ __forceinline__ T *get(size_t n) {
+        T *p = reinterpret_cast<T *>(base + used);
+        used += (n * sizeof(T) + 15) & ~size_t(15);
+        ok = ok && used <= cap;
+        return p;
+    }
+};
+
 #define DECL_LOCI                                                                                   \
-    int *l_lo = ar.get<int>(Graw), *l_len = ar.get<int>(Graw), *l_raw = ar.get<int>(Graw);          \
-    int *l_base = ar.get<int>(Graw + 2);                                                            \
-    const u16 **l_plan = ar.get<const u16 *>(Graw + 1);                                             \
-    int *l_nleaf = ar.get<int>(Graw + 1);                                                           \
-    signed char *l_str = ar.get<signed char>(Graw);                                                 \
-    u32 *l_k8 = ar.get<u32>(Graw + 1);
+    int *l_lo = arA.get<int>(Graw), *l_len = arA.get<int>(Graw), *l_raw = arA.get<int>(Graw);       \
+    int *l_base = arA.get<int>(Graw + 2);                                                           \
+    const u16 **l_plan = arA.get<const u16 *>(Graw + 1);                                            \
+    int *l_nleaf = arA.get<int>(Graw + 1);                                                          \
+    signed char *l_str = arA.get<signed char>(Graw);                                                \
+    u32 *l_k8 = arA.get<u32>(Graw + 1);
 
 #define DECL_RECORDS                                                                                \
     u16 *plan_fb = ar.get<u16>(np_tot);                                                             \
@@ -150,7 +172,7 @@ namespace {
     double *g_score = al.get<double>(Ngrp);                                                         \
     int *g_rs = al.get<int>(Ngrp + 1), *g_re = al.get<int>(Ngrp + 1), *g_loc = al.get<int>(Ngrp),   \
         *g_t = al.get<int>(Ngrp), *gs = al.get<int>(ng + 1), *g_perm = al.get<int>(Ngrp),           \
-        *gcur = al.get<int>(G + 2);
+        *gcur = al.get<int>(2 * G + 2);
 
 #define DECL_CLADES                                                                                 \
     int *cl_go = al.get<int>(T + 1), *cand = al.get<int>(T);                                        \
@@ -185,7 +207,7 @@ __device__ __forceinline__ size_t record_bytes(int M, int G, int W, int S, int n
 // region C: bound on the per-level arrays once the number of distinct clades T is known
 __device__ __forceinline__ size_t level_bytes(int T, int M, int G, int W) {
     size_t t = (size_t)T, ngb = (size_t)min((long long)M, (long long)T * G) + (size_t)G + 1;
-    return al16(4 * (t + 2)) + 16 * (size_t)M + 48 + 40 * ngb + al16(4 * ((size_t)G + 2)) + 160 + 27 * t + 24 * (size_t)W * t + 24 * (size_t)W +
+    return al16(4 * (t + 2)) + 16 * (size_t)M + 48 + 40 * ngb + al16(4 * (2 * (size_t)G + 2)) + 160 + 27 * t + 24 * (size_t)W * t + 24 * (size_t)W +
            256 + sizeof(Level) + al16(4 * (t + 1)) + 16 * 25 + 6144;
 }
 
@@ -252,11 +274,11 @@ __device__ __forceinline__ long long pop_work(unsigned long long *wq, const int 
     (void)H; (void)h0;                                                                              \
     const int G = cx.G, W = cx.W, M = cx.M, np_tot = cx.np_tot, iter = cx.iter;                     \
     int T = cx.T, lifts = cx.lifts;                                                                 \
-    Arena ar{a.pool + cx.offA, a.pool + cx.offB, (size_t)cx.capA, (size_t)cx.capB, 0, 0, true, true}; \
+    LinArena arA{a.pool + cx.offA, (size_t)cx.capA, 0, true};                                       \
+    LinArena ar{a.pool + cx.offB, (size_t)cx.capB, 0, true};                                        \
     DECL_LOCI                                                                                       \
     DECL_RECORDS                                                                                    \
-    Arena al{a.pool + cx.offB + ar.slab_used, a.pool + cx.offC, (size_t)cx.capB - ar.slab_used, (size_t)cx.capC, \
-             0, 0, true, true};                                                                     \
+    LinArena al{a.pool + cx.offC, (size_t)cx.capC, 0, true};                                        \
     (void)l_lo; (void)l_base; (void)l_plan; (void)l_nleaf; (void)l_str; (void)l_k8; (void)plan_fb;  \
     (void)r_a; (void)r_b; (void)r_hit; (void)base_ord; (void)maxv; (void)annb; (void)annw; (void)map_t; (void)fo; \
     (void)r_v; (void)ord; (void)maxb; (void)iter;
@@ -294,8 +316,10 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
         if (lane == 0) offA = atomicAdd(a.pool_used, (unsigned long long)((capA + 255) & ~size_t(255)));
         offA = __shfl_sync(FULL, offA, 0);
         const bool fitsA = offA + capA <= a.pool_cap;
-        Arena ar{a.pool + (fitsA ? offA : 0), nullptr, fitsA ? capA : 0, 0, 0, 0, true, true};
+        LinArena arA{a.pool + (fitsA ? offA : 0), fitsA ? capA : 0, 0, true};
+        LinArena ar{a.pool, 0, 0, true};
         DECL_LOCI
+        if (!fitsA) arA.ok = false;
 @A@
         __syncwarp();
         const int W = (G + 63) >> 6;
@@ -311,18 +335,17 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
             if (lane == 0) offB = atomicAdd(a.pool_used, (unsigned long long)((capB + 255) & ~size_t(255)));
             offB = __shfl_sync(FULL, offB, 0);
             if (offB + capB <= a.pool_cap) {
-                ar.slab = a.pool + offB;
-                ar.slab_cap = capB;
+                ar.base = a.pool + offB;
+                ar.cap = capB;
+            } else {
+                ar.ok = false;
             }
             DECL_RECORDS
             overflow = !ar.ok;
             if (!overflow) {
 @C@
 @E@
-                const size_t mark_smem = ar.smem_used, mark_slab = ar.slab_used;
 @D@
-                ar.smem_used = mark_smem;
-                ar.slab_used = mark_slab;
             }
             const bool bad = __any_sync(FULL, bad_input);
             if (!overflow && !bad) {

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     double *g_score = ar.get<double>(Ngrp);
                     int *g_rs = ar.get<int>(Ngrp + 1), *g_re = ar.get<int>(Ngrp + 1), *g_loc = ar.get<int>(Ngrp),
                         *g_t = ar.get<int>(Ngrp), *gs = ar.get<int>(ng + 1),
-                        *g_perm = ar.get<int>(Ngrp), *gcur = ar.get<int>(G + 2);
+                        *g_perm = ar.get<int>(Ngrp), *gcur = ar.get<int>(2 * G + 2);
                     if (!ar.ok) { overflow = true; break; }
                     int gbase = 0;
 #pragma unroll 1
@@ -500,8 +500,17 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     __syncwarp();
                     PH(2);
                     // ---- K2: envelope integral per group, numpy-pairwise-exact ----------------------
-                    // groups are visited locus-major so that the lanes of a warp walk the same leaf plan
-                    warp_multisplit(Ngrp, G, g_loc, nullptr, gcur, g_perm);
+                    // groups are visited multi-record groups first, then single-record ones, locus-major inside
+                    // each class: lanes of a warp then walk the same leaf plan and meet groups of similar
+                    // envelope complexity (leaves with several run boundaries are the expensive, divergent part)
+                    {
+                        int *gkey = reinterpret_cast<int *>(g_score);   // g_score is written only below
+#pragma unroll 1
+                        for (int g = lane; g < Ngrp; g += 32)
+                            gkey[g] = g_loc[g] + ((g_rs[g] >= 0 && g_re[g] - g_rs[g] >= 2) ? 0 : G);
+                        __syncwarp();
+                        warp_multisplit(Ngrp, 2 * G, gkey, nullptr, gcur, g_perm);
+                    }
                     __syncwarp();
 #pragma unroll 1
                     for (int base = 0; base < Ngrp; base += 32) {
