@@ -88,7 +88,7 @@ L2 = L2.replace("""                        size_t room = (al.smem_cap - al.smem_
 """)
 L2 = L2.replace("Arena ax = al;", "LinArena ax = al;").replace("ax = Arena{a.pool + off, nullptr, (size_t)want, 0, 0, 0, true, true};", "ax = LinArena{a.pool + off, (size_t)want, 0, true};")
 L2 = L2.replace("long long scap = (long long)(room / 16) - 8;",
-                "long long scap = ((long long)room - 4LL * (T + 1) - 256) / 16;   // leave room for the lift's parent table")
+                "long long scap = ((long long)room - 4LL * (T + 1) - 8LL * (BITMAP_MAX_WORDS >= ((tax.n_nodes + 31) >> 5) ? ((tax.n_nodes + 31) >> 5) : 0) - 512) / 16;   // leave room for the lift's tables")
 assert "LinArena ax = al;" in L2 and "al.cap - al.used" in L2 and "4LL * (T + 1)" in L2
 Mm = Mm  # members block touches no arena
 
@@ -181,6 +181,7 @@ struct LinArena {
     u64 *mk0 = al.get<u64>((size_t)T * W), *mk1 = al.get<u64>((size_t)T * W),                       \
         *mk2 = al.get<u64>((size_t)T * W);                                                          \
     u64 *bestm = al.get<u64>(3 * (size_t)W);                                                        \
+    int *cl_par = al.get<int>(T);                                                                   \
     Level *Lp = al.get<Level>(1);
 
 __device__ __forceinline__ size_t al16(size_t b) { return (b + 15) & ~size_t(15); }
@@ -205,10 +206,11 @@ __device__ __forceinline__ size_t record_bytes(int M, int G, int W, int S, int n
     return p + (nwords <= BITMAP_MAX_WORDS ? bitmap_tmp : hash_tmp);
 }
 // region C: bound on the per-level arrays once the number of distinct clades T is known
-__device__ __forceinline__ size_t level_bytes(int T, int M, int G, int W) {
+__device__ __forceinline__ size_t level_bytes(int T, int M, int G, int W, int nwords) {
     size_t t = (size_t)T, ngb = (size_t)min((long long)M, (long long)T * G) + (size_t)G + 1;
     return al16(4 * (t + 2)) + 16 * (size_t)M + 48 + 40 * ngb + al16(4 * (2 * (size_t)G + 2)) + 160 + 27 * t + 24 * (size_t)W * t + 24 * (size_t)W +
-           256 + sizeof(Level) + al16(4 * (t + 1)) + 16 * 25 + 6144;
+           256 + sizeof(Level) + al16(4 * (t + 1)) + 4 * t + 16 * 25 + 6144 +
+           (((size_t)nwords <= (size_t)BITMAP_MAX_WORDS) ? 8 * (size_t)nwords + 96 : 0);
 }
 
 struct ContigOut {
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
             const bool bad = __any_sync(FULL, bad_input);
             if (!overflow && !bad) {
                 // region C: per-level arrays, sized now that T is known
-                const size_t capC = level_bytes(T, M, G, W);
+                const size_t capC = level_bytes(T, M, G, W, (tax.n_nodes + 31) >> 5);
                 unsigned long long offC = 0;
                 if (lane == 0) offC = atomicAdd(a.pool_used, (unsigned long long)((capC + 255) & ~size_t(255)));
                 offC = __shfl_sync(FULL, offC, 0);
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_one(const PipeArgs
         DECL_GROUPS
         DECL_CLADES
         (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
-        (void)cand; (void)memB; (void)mk1; (void)mk2; (void)bestm; (void)cl_go;
+        (void)cand; (void)memB; (void)mk1; (void)mk2; (void)bestm; (void)cl_go; (void)cl_par;
         const Level &L = *Lp;
         (void)L;
 @J@
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
         DECL_GROUPS
         DECL_CLADES
         (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
-        (void)cl_rank; (void)cl_crit; (void)cl_opt; (void)mk0; (void)mk2; (void)cl_go;
+        (void)cl_rank; (void)cl_crit; (void)cl_opt; (void)mk0; (void)mk2; (void)cl_go; (void)cl_par;
         const Level &L = *Lp;
         bool overflow = false, lifted = false;
         unsigned long long need_hint = 0;

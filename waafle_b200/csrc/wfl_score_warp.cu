@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     u64 *mk0 = ar.get<u64>((size_t)T * W), *mk1 = ar.get<u64>((size_t)T * W),
                         *mk2 = ar.get<u64>((size_t)T * W);
                     u64 *bestm = ar.get<u64>(3 * (size_t)W);
+                    int *cl_par = ar.get<int>(T);   // parent of each listed clade of the contig, -1 if unlisted
                     Level *Lp = ar.get<Level>(1);
                     if (!ar.ok) { overflow = true; break; }
 #pragma unroll 1
@@ -589,6 +590,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
 #pragma unroll 1
                     for (int t = lane; t < T; t += 32) {
                         memA[t] = memB[t] = 0;
+                        cl_par[t] = tax.listed[cl_id[t]] ? tax.parent[cl_id[t]] : -1;
 #pragma unroll 1
                         for (int q = 0; q < 3; ++q) {
                             u64 *m = (q == 0 ? mk0 : q == 1 ? mk1 : mk2) + (size_t)t * W;
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) *Lp = Level{G, W, T, Ngrp, nun, g_loc, g_score, cl_id, cl_go, {mk0, mk1, mk2}, um, ign, l_len};
+                    if (lane == 0) *Lp = Level{G, W, T, Ngrp, nun, g_loc, g_score, cl_id, cl_go, {mk0, mk1, mk2}, um, ign, l_len, cl_par};
                     __syncwarp();
                     const Level &L = *Lp;
                     PH(4);
@@ -872,6 +874,33 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         if (lane == 0) par[T] = spike ? tax.unknown : -1;   // re-inserted spike key
                         __syncwarp();
                         int Tn = 0;
+                        const int nwl = (tax.n_nodes + 31) >> 5;
+                        if (nwl <= BITMAP_MAX_WORDS) {
+                            // small taxonomies: presence bitmap of the parents, new rank = prefix popcount
+                            u32 *bm = ar.get<u32>(nwl);
+                            int *bpre = ar.get<int>(nwl + 1);
+                            if (!ar.ok) { overflow = true; break; }
+#pragma unroll 1
+                            for (int w = lane; w < nwl; w += 32) bm[w] = 0;
+                            __syncwarp();
+#pragma unroll 1
+                            for (int t = lane; t <= T; t += 32)
+                                if (par[t] >= 0) atomicOr(&bm[par[t] >> 5], 1u << (par[t] & 31));
+                            __syncwarp();
+#pragma unroll 1
+                            for (int base = 0; base < nwl; base += 32) {
+                                const int w = base + lane;
+                                int tot, ex = warp_excl_scan(w < nwl ? __popc(bm[w]) : 0, tot);
+                                if (w < nwl) bpre[w] = Tn + ex;
+                                Tn += tot;
+                            }
+                            __syncwarp();
+#pragma unroll 1
+                            for (int t = lane; t <= T; t += 32) {
+                                const int key = par[t];
+                                map_t[t] = key < 0 ? -1 : bpre[key >> 5] + __popc(bm[key >> 5] & ((1u << (key & 31)) - 1u));
+                            }
+                        } else {
 #pragma unroll 1
                         for (int base = 0; base <= T; base += 32) {   // first occurrences of each key
                             int t = base + lane;
@@ -895,6 +924,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                                 for (int q = 0; q <= T; ++q) rk += fo[q] && par[q] < key;
                             }
                             map_t[t] = rk;
+                        }
                         }
                         __syncwarp();
 #pragma unroll 1

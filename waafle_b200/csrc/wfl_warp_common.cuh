@@ -549,6 +549,7 @@ struct Level {   // per-level views shared by the search routines (all pointers 
     const u64 *um;      // non-ignored loci
     const u8 *ign;
     const int *l_len;
+    const int *cl_par;   // parent of each listed clade (get_sisters works on the taxonomy file's rows), else -1
 };
 
 __device__ __noinline__ double score_clades(const Level *L, int t1, int t2, double *crit_out) {
@@ -641,12 +642,10 @@ __device__ __noinline__ void eval_two(const Level &L, const DevTax &tax, const D
         const int p1 = tax.parent[ev.c1], p2 = tax.parent[ev.c2];
 #pragma unroll 1
         for (int t = 0; t < L.T && ok; ++t) {
-            int x = L.cl_id[t];
-            if (x == ev.c1 || x == ev.c2 || !tax.listed[x]) continue;
-            int px = tax.parent[x];
-            bool s1 = px == p1, s2 = (px == p2) && !ev.dir;
+            const int px = L.cl_par[t];
+            const bool s1 = px == p1, s2 = (px == p2) && !ev.dir;
             if (!s1 && !s2) continue;
-#pragma unroll 1
+            if (t == ev.t1 || t == ev.t2) continue;
             for (int w = 0; w < L.W; ++w) {
                 u64 A, B, amb;
                 letters(L, mamb, unk, ta, tb, w, A, B, amb);
