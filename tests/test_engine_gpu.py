@@ -178,6 +178,30 @@ def test_full_size_properties(engine):
         assert not helpers.compare_results(ref, got)
 
 
+def test_tree_walk_gene_scores_bit_exact(monkeypatch):
+    """WFL_K2=tree: the gene-score sums by tree walk with constant-subtree skipping (experimental,
+    slower on B200) must reproduce the flat leaf-plan walk bit for bit."""
+    from waafle_b200 import synth
+    from waafle_b200.engine import Engine
+    data = synth.generate_config("cfg2", n_contigs=500, seed=63)
+    tax = data.taxonomy()
+    batch = data.to_batch(tax)
+    P = helpers.params_for({}, 0)
+    outs = []
+    for k2 in ("leaf", "tree"):
+        monkeypatch.setenv("WFL_K2", k2)
+        eng = Engine(0, P, tax)
+        outs.append(eng.score_batch(batch))
+        eng.close()
+    assert not helpers.compare_results(outs[0], outs[1])
+    batch2, tax2 = helpers.adversarial_batches()["knife_edge"]
+    eng = Engine(0, helpers.params_for({}, 1), tax2)
+    got = eng.score_batch(batch2)
+    eng.close()
+    ref = oracle.score_batch(helpers.params_for({}, 1).as_dict(), tax2.tables(), batch2.arrays())
+    assert not helpers.compare_results(ref, got)
+
+
 @pytest.mark.parametrize("mode", ["v2", "v1"])
 def test_alternate_kernels_stay_bit_exact(mode, monkeypatch):
     """The monolithic warp kernel (v2: also the replay path for contigs that outgrow the pipeline's

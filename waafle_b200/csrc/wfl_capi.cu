@@ -41,11 +41,13 @@ struct wfl_engine {
     int threads = 32, smem_bytes = 10 * 1024, ctas_per_sm = 12;
     size_t slab_bytes = 256 * 1024;
     // device buffers (grow-only)
-    Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
+    Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data, plan_tree;
     int plan_nmax = 0;
     // multi-kernel pipeline state
     int mode = 2;                       // 0: v1 CTA-per-contig, 1: v2 monolithic warp kernel, 2: pipeline
     int tax_max_depth = 0;
+    bool use_tree = false;              // WFL_K2=tree: K2 by tree walk with constant-subtree skipping (parity-tested,
+                                        // but slower than the flat leaf plan on B200: more local-memory state)
     size_t pipe_pool_bytes = size_t(8192) << 20;
     Buf pipe_pool, pipe_ctg, pipe_lists, pipe_cnt, pipe_wq;
     std::vector<int64_t> h_hit_off, h_locus_off;
@@ -145,6 +147,40 @@ void host_build_plan(int n, std::vector<uint16_t> &data, PlanEntry &pe) {
     pe.k8 = (uint32_t)k8[0] | ((uint32_t)k8[1] << 8) | ((uint32_t)k8[2] << 16) | ((uint32_t)k8[3] << 24);
 }
 
+
+// Distinct node sizes of the split tree of an n-element sum, ascending, children by index.
+void host_build_tree(int n, std::vector<TreeEntry> &data, PlanEntry &pe) {
+    std::vector<int> sizes;
+    std::vector<int> todo{n};
+    while (!todo.empty()) {
+        int m = todo.back();
+        todo.pop_back();
+        if (std::find(sizes.begin(), sizes.end(), m) != sizes.end()) continue;
+        sizes.push_back(m);
+        if (m > 128) {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            todo.push_back(n2);
+            todo.push_back(m - n2);
+        }
+    }
+    std::sort(sizes.begin(), sizes.end());
+    pe.toff = (uint32_t)data.size();
+    pe.nsz = (uint32_t)sizes.size();
+    for (int m : sizes) {
+        TreeEntry t;
+        t.size = (uint16_t)m;
+        t.li = t.ri = 255;
+        if (m > 128) {
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            t.li = (uint8_t)(std::find(sizes.begin(), sizes.end(), n2) - sizes.begin());
+            t.ri = (uint8_t)(std::find(sizes.begin(), sizes.end(), m - n2) - sizes.begin());
+        }
+        data.push_back(t);
+    }
+}
+
 // Leaf plans for every gene length up to `want` (capped): built once, kept on the device.
 int ensure_plan_table(wfl_engine *e, int want) {
     const int cap = 16384;
@@ -154,12 +190,20 @@ int ensure_plan_table(wfl_engine *e, int want) {
     std::vector<uint16_t> data;
     data.reserve((size_t)want * want / 150 + 1024);
     index[0] = PlanEntry{0, 0, 0};
-    for (int n = 1; n <= want; ++n) host_build_plan(n, data, index[n]);
+    std::vector<TreeEntry> tdata;
+    tdata.reserve((size_t)want * 18);
+    index[0].toff = index[0].nsz = 0;
+    for (int n = 1; n <= want; ++n) {
+        host_build_plan(n, data, index[n]);
+        host_build_tree(n, tdata, index[n]);
+    }
     const PlanEntry *di;
     const uint16_t *dd;
     int rc;
     if ((rc = upload(e, e->plan_index, index.data(), index.size(), &di))) return rc;
     if ((rc = upload(e, e->plan_data, data.data(), data.size(), &dd))) return rc;
+    const TreeEntry *dt;
+    if ((rc = upload(e, e->plan_tree, tdata.data(), tdata.size(), &dt))) return rc;
     CU(cudaStreamSynchronize(e->stream));
     e->plan_nmax = want;
     return WFL_OK;
@@ -247,7 +291,7 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     pa.b = sa.b; pa.t = sa.t; pa.o = sa.o; pa.P = sa.P; pa.ctr = sa.ctr;
     pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool.cap;
     pa.ctg = ctg;
-    pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data;
+    pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data; pa.plan_tree = sa.plan_tree;
     pa.dbg_contig = -1;
     int *list[3] = {lists, lists + n, lists + 2 * n};
     int *cnt_act = cnt, *cnt_two = cnt + 66;
@@ -333,6 +377,7 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
         a.plan_nmax = e->plan_nmax;
         a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
         a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
+        a.plan_tree = e->use_tree ? static_cast<const TreeEntry *>(e->plan_tree.p) : nullptr;
         a.dbg_contig = -1;
         if (attempt == 0 && e->n > 0 && (src != nullptr || e->mode == 2)) {
             // The batch is cut into chunks of contigs.  Plugin call (src != nullptr): chunk k+1 crosses
@@ -639,6 +684,7 @@ int wfl_create(int device, wfl_engine **out) {
         e->mode = m == "v1" ? 0 : m == "v2" ? 1 : 2;
     }
     if (e->mode == 0) { e->threads = 128; e->smem_bytes = 36 * 1024; e->ctas_per_sm = 6; }
+    if (const char *k = getenv("WFL_K2")) e->use_tree = std::string(k) == "tree";
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
     if (const char *k = getenv("WFL_CHUNK_MB")) e->chunk_bytes = (size_t)atoll(k) << 20;
     e->smem_optin = prop.sharedMemPerBlockOptin;
@@ -660,7 +706,7 @@ void wfl_destroy(wfl_engine *e) {
     for (auto &b : e->out) fr(b);
     for (auto &b : e->cm) fr(b);
     for (auto &b : e->dbg) fr(b);
-    fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data);
+    fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data); fr(e->plan_tree);
     fr(e->pipe_pool); fr(e->pipe_ctg); fr(e->pipe_lists); fr(e->pipe_cnt); fr(e->pipe_wq);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->chunk_ev) cudaEventDestroy(ev);
@@ -829,6 +875,7 @@ int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int
     a.work_list = wl; a.n_work = 1; a.slab = slab; a.slab_bytes = slab_bytes; a.smem_bytes = e->smem_bytes;
     a.plan_nmax = e->plan_nmax; a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
     a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
+    a.plan_tree = e->use_tree ? static_cast<const TreeEntry *>(e->plan_tree.p) : nullptr;
     a.dbg_contig = contig; a.dbg_clade = dc; a.dbg_locus = dl; a.dbg_score = ds; a.dbg_cap = capacity; a.dbg_count = dn;
     if (e->mode != 0)
         launch_score_kernel_warp(a, 1, e->stream);

@@ -70,6 +70,14 @@ struct DevParams {
 // distinct m/8 values (ascending, 0 = unused / memo disabled).
 struct PlanEntry {
     uint32_t off, nleaf, k8;
+    uint32_t toff, nsz;   // node-size table of the same tree (TreeEntry[nsz], ascending size, root last)
+};
+
+// One distinct node size of the pairwise split tree: a node of `size` > 128 elements splits into
+// nodes li / ri (indices into the same table); li == ri == 255 marks a leaf (size <= 128).
+struct TreeEntry {
+    uint16_t size;
+    uint8_t li, ri;
 };
 
 struct ScoreArgs {
@@ -88,6 +96,7 @@ struct ScoreArgs {
     int plan_nmax;
     const PlanEntry *plan_index;   // [plan_nmax + 1]
     const uint16_t *plan_data;
+    const TreeEntry *plan_tree;
     // test hook: dump the level-0 gene scores of one contig as COO triples
     long long dbg_contig;       // -1 = off
     int32_t *dbg_clade, *dbg_locus;
@@ -129,6 +138,7 @@ struct PipeArgs {
     int plan_nmax;
     const PlanEntry *plan_index;
     const uint16_t *plan_data;
+    const TreeEntry *plan_tree;
     long long dbg_contig;
     int32_t *dbg_clade, *dbg_locus;
     double *dbg_score;

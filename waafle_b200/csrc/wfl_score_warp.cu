@@ -174,8 +174,13 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                     const int len = l_len[i];
                     if (len <= a.plan_nmax) {
                         const PlanEntry pe = a.plan_index[len];
-                        l_plan[i] = a.plan_data + pe.off;
-                        l_nleaf[i] = (int)pe.nleaf;
+                        if (a.plan_tree != nullptr) {   // node-size table (tree walk); nleaf < 0 flags it
+                            l_plan[i] = reinterpret_cast<const u16 *>(a.plan_tree + pe.toff);
+                            l_nleaf[i] = -(int)pe.nsz;
+                        } else {
+                            l_plan[i] = a.plan_data + pe.off;
+                            l_nleaf[i] = (int)pe.nleaf;
+                        }
                         l_k8[i] = pe.k8;
                     } else {
                         u16 *dst = plan_fb + l_nleaf[i];

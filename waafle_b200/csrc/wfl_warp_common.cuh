@@ -422,10 +422,111 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
     return res;
 }
 
+// Tree walk of the same sum.  numpy's split depends only on the node size, so the tree of an n-element
+// sum has a handful of distinct node sizes (<= 23 for n <= 16384; host-built table, children by index).
+// A node that lies inside ONE envelope run is a sum over a constant array: its value C(size, v) is
+// computed once per run for every table entry (leaves by add chain, inner nodes C(l) + C(r)) and whole
+// subtrees are skipped; only the leaves that straddle a run boundary are evaluated per column.
+__device__ __noinline__ double group_mean_tree(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
+                                               bool sorted, const TreeEntry *te, int nsz) {
+    Site s;
+    s.ra = ra; s.rb = rb; s.rv = rv;
+    s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
+    s.k8[0] = s.k8[1] = s.k8[2] = s.k8[3] = 0;
+    s.pos = 0;
+    s.run_end = 0;
+    s.memo_ok = false;
+    double Cv[24];
+    int cv_run = -1;   // Cv holds C(size, run_v) of the run that ends at cv_run
+    unsigned char sidx[12], sst[12];
+    int spos[12];
+    double sacc[12];
+    int sp = 0;
+    sidx[0] = (unsigned char)(nsz - 1);
+    spos[0] = 0;
+    sst[0] = 0;
+    double ret = 0.0;
+    bool returning = false;
+#pragma unroll 1
+    for (;;) {
+        if (!returning) {
+            const TreeEntry e = te[sidx[sp]];
+            const int m = e.size, p = spos[sp];
+            s.pos = p;   // nodes are visited left to right
+            if (s.pos >= s.run_end) s.advance();
+            if (s.run_end - p >= m) {
+                // the node lies inside one run
+                if (s.run_v == 0.0) {
+                    ret = 0.0;
+                } else {
+                    if (cv_run != s.run_end) {
+                        const double v = s.run_v;
+                        double c = v;
+                        int ck = 1;
+#pragma unroll 1
+                        for (int j = 0; j < nsz; ++j) {
+                            const TreeEntry ej = te[j];
+                            double r;
+                            if (ej.li == 255) {
+                                const int mm = ej.size;
+                                if (mm < 8) {
+                                    r = 0.0;
+#pragma unroll 1
+                                    for (int i = 0; i < mm; ++i) r += v;
+                                } else {
+                                    const int k = mm >> 3;   // ascending with j: extend the add chain S_k(v)
+#pragma unroll 1
+                                    for (; ck < k; ++ck) c += v;
+                                    r = 8.0 * c;             // eight equal lanes: the fold is exact
+#pragma unroll 1
+                                    for (int i = 0; i < (mm & 7); ++i) r += v;
+                                }
+                            } else {
+                                r = Cv[ej.li] + Cv[ej.ri];
+                            }
+                            Cv[j] = r;
+                        }
+                        cv_run = s.run_end;
+                    }
+                    ret = Cv[sidx[sp]];
+                }
+                returning = true;
+                if (--sp < 0) break;
+            } else if (e.li == 255) {
+                ret = mixed_leaf(s, m);   // a leaf that straddles a run boundary
+                returning = true;
+                if (--sp < 0) break;
+            } else {
+                sst[sp] = 1;
+                ++sp;
+                sidx[sp] = e.li;
+                spos[sp] = p;
+                sst[sp] = 0;
+            }
+        } else if (sst[sp] == 1) {
+            const TreeEntry e = te[sidx[sp]];
+            sacc[sp] = ret;
+            sst[sp] = 2;
+            const int p = spos[sp] + te[e.li].size;
+            ++sp;
+            sidx[sp] = e.ri;
+            spos[sp] = p;
+            sst[sp] = 0;
+            returning = false;
+        } else {
+            ret = sacc[sp] + ret;
+            if (--sp < 0) break;
+        }
+    }
+    return ret / (double)n;
+}
+
 // np.mean of the group's site array (waafle_orgscorer.py:403) without materialising it.
 // ra/rb/rv[rs..re) are the group's records (in descending score order if `sorted`).
 __device__ __noinline__ double group_mean(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
                                           bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
+    if (nleaf < 0)   // tree mode: `plan` is the node-size table of this gene length
+        return group_mean_tree(ra, rb, rv, rs, re, n, sorted, reinterpret_cast<const TreeEntry *>(plan), -nleaf);
     Site s;
     s.ra = ra; s.rb = rb; s.rv = rv;
     s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
