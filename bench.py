@@ -183,7 +183,7 @@ def main():
     batch, params, tax = make_workload(args, rank)
 
     # ---- CPU baseline beside the GPU numbers (rank 0, N=1 only, before any CUDA init) ----
-    cpu_baseline = None
+    cpu_baseline, c_ref = None, None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         per_core = {"cfg2": 1500, "cfg3": 600, "cfg5": 600, "cfg4": 4}.get(args.workload, 300)
@@ -192,6 +192,19 @@ def main():
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
                         "sample": "first {} contigs of the workload, numpy oracle, {} processes, {:.1f} s wall"
                                   .format(min(n_sample, batch.n_contigs), used, wall)}
+
+        # second CPU arm: the C restatement (oracle/orgscorer_oracle.c), one thread per core, on the WHOLE
+        # workload; its output doubles as the full-size parity reference for the GPU results below
+        try:
+            from oracle import c_oracle
+            tc = time.perf_counter()
+            c_ref = c_oracle.score_batch(params, tax, batch, threads=cores)
+            wall_c = time.perf_counter() - tc
+            cpu_baseline["c_port"] = {"value": batch.n_contigs / wall_c, "unit": UNIT, "cores": cores,
+                                      "sample": "all {} contigs, C restatement of the reference, {} threads, "
+                                                "{:.1f} s wall".format(batch.n_contigs, cores, wall_c)}
+        except Exception as exc:   # the checker failing to build must not hide the GPU numbers
+            cpu_baseline["c_port"] = {"unavailable": repr(exc)[:200]}
 
     import torch
     torch.cuda.set_device(local_rank)
@@ -229,6 +242,13 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - t0)
     res = eng.download()
     st = eng.stats()
+    parity = None
+    if c_ref is not None:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import compare_results
+        diffs = compare_results(c_ref, res)
+        parity = {"checked_contigs": batch.n_contigs, "against": "oracle/orgscorer_oracle.c",
+                  "bit_exact": not diffs, "diffs": [str(d)[:160] for d in diffs[:3]]}
 
     # ---- end-to-end leg: pinned host buffers through the plugin call ----
     from waafle_b200.engine import PinnedArena
@@ -307,6 +327,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms": score_ms / args.steps},
             "cpu_baseline": cpu_baseline,
+            "parity": parity,
             "clocks": sampler.summary(),
             "calls": {"lgt": int(res["call_counts"][0]), "no_lgt": int(res["call_counts"][1]),
                       "unclassified": int(res["call_counts"][2])},

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import helpers
+from oracle import c_oracle
 from oracle import orgscorer_oracle as oracle
 from oracle.validate_against_reference import FLAG_SETS, compare_records, records_from_results
 
@@ -176,6 +177,28 @@ def test_full_size_properties(engine):
         ref = oracle.score_batch(P.as_dict(), tax.tables(), sub.arrays())
         got = engine.score_batch(sub)
         assert not helpers.compare_results(ref, got)
+
+
+@pytest.mark.parametrize("config,n,flags", [
+    ("cfg2", None, {}),                                        # BASELINE configs[1] at full size: 100k contigs
+    ("cfg2", 30000, dict(weak_loci="penalize", range=0.3, allow_lca=True)),
+    ("cfg3", 30000, {}),                                       # configs[2] shape, 8 levels
+    ("cfg5", 20000, dict(weak_loci="assign-unknown")),         # configs[4] shape, annotations
+    ("cfg4", 24, dict(sister_penalty="off")),                  # configs[3] shape: 100+ genes, 550 taxa
+])
+def test_full_size_bit_exact_vs_c_oracle(engine, config, n, flags):
+    """Every contig of the full-size workloads, every output byte, against the C restatement of the
+    reference (oracle/orgscorer_oracle.c, itself pinned to the numpy oracle in tests/test_c_oracle.py)."""
+    from waafle_b200 import synth
+    data = synth.generate_config(config, n_contigs=n, seed=1000, annotations=(config == "cfg5"))
+    tax = data.taxonomy()
+    batch = data.to_batch(tax)
+    P = helpers.params_for(flags, 1 if config == "cfg5" else 0)
+    got = run_engine(engine, P, tax, batch)
+    ref = c_oracle.score_batch(P, tax, batch)
+    diffs = helpers.compare_results(ref, got)
+    assert not diffs, diffs[:4]
+    assert got["call_counts"].sum() == batch.n_contigs
 
 
 def test_tree_walk_gene_scores_bit_exact(monkeypatch):
