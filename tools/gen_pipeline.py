@@ -401,11 +401,13 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeA
         RESULT_LOCALS
         bool overflow = false, cont_ok = false;
         int Ngrp = 0, ng = 0, nlt = 0, nu = 0, t_unk = -1, nun = 0, hasroot = 0;
-        long long n_groups = 0;
+        long long n_groups = 0, t_f = 0, t_g = 0;
 #pragma unroll 1
         for (int once = 0; once < 1; ++once) {
 @F@
+            t_f = clock64();
 @G2@
+            t_g = clock64();
 @H@
 @I@
             cont_ok = true;
@@ -413,7 +415,14 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeA
         if (lane == 0) {
             atomicAdd(&a.ctr->groups, (unsigned long long)n_groups);
             atomicAdd(&a.ctr->levels, 1ull);
-            atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(clock64() - t_start));
+            const long long t_end = clock64();
+            if (t_g) {   // sub-phases: regroup + group table | K2 envelope integrals | weak loci + masks
+                atomicAdd(&a.ctr->phase_cycles[2], (unsigned long long)(t_f - t_start));
+                atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(t_g - t_f));
+                atomicAdd(&a.ctr->phase_cycles[4], (unsigned long long)(t_end - t_g));
+            } else {
+                atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(t_end - t_start));
+            }
         }
         if (overflow) {
             EMIT_RESULT(1);
