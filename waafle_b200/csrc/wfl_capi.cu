@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -25,10 +26,12 @@ struct wfl_engine {
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_join = nullptr;
+    int n_slots = 2;                     // plugin call: sub-batches alternate between two compute streams
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> chunk_ev;
-    size_t chunk_bytes = size_t(128) << 20;  // H2D chunk size of the pipelined plugin call
+    size_t chunk_bytes = size_t(64) << 20;   // H2D chunk size of the pipelined plugin call (measured best: profiles/README.md)
     std::string err;
     bool have_params = false, have_tax = false, have_batch = false, have_results = false;
     DevParams P{};
@@ -49,13 +52,27 @@ struct wfl_engine {
     bool use_tree = false;              // WFL_K2=tree: K2 by tree walk with constant-subtree skipping (parity-tested,
                                         // but slower than the flat leaf plan on B200: more local-memory state)
     size_t pipe_pool_bytes = size_t(8192) << 20;
-    Buf pipe_pool, pipe_ctg, pipe_lists, pipe_cnt, pipe_wq;
+    Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2];
     std::vector<int64_t> h_hit_off, h_locus_off;
+    std::vector<int64_t> chunks;         // contig boundaries of the sub-batches of the current batch
+    bool chunks_streamed = false;        // their H2D copies are in flight on copy_stream (plugin call)
+    double chunk_shrink = 1.0;           // < 1: geometric tail of the streaming schedule, each chunk >= shrink * its
+                                         // predecessor (WFL_CHUNK_SHRINK; measured no better than equal chunks)
     wfl_stats stats{};
     int64_t members_total = 0;
 };
 
 namespace {
+
+// WFL_TRACE=1: host-side timeline of a plugin call on stderr (milliseconds since the call started)
+static bool g_trace = getenv("WFL_TRACE") != nullptr;
+static std::chrono::steady_clock::time_point g_t0;
+static void trace(const char *what) {
+    if (!g_trace) return;
+    if (!strcmp(what, "begin")) g_t0 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[wfl] %8.3f ms  %s\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count(), what);
+}
 
 bool set_err(wfl_engine *e, const char *fmt, ...) {
     char buf[512];
@@ -89,10 +106,10 @@ int ensure(wfl_engine *e, Buf &b, size_t bytes) {
 }
 
 template <class T>
-int upload(wfl_engine *e, Buf &b, const T *src, size_t n, const T **dst) {
+int upload(wfl_engine *e, Buf &b, const T *src, size_t n, const T **dst, cudaStream_t st = nullptr) {
     int rc = ensure(e, b, n * sizeof(T));
     if (rc) return rc;
-    if (n) CU(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    if (n) CU(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st ? st : e->stream));
     *dst = static_cast<const T *>(b.p);
     return WFL_OK;
 }
@@ -271,8 +288,95 @@ int alloc_outputs(wfl_engine *e) {
 
 int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all);
 
+// Cut the batch into sub-batches of whole contigs.
+//  * pipeline mode: a sub-batch's intermediate state must fit the workspace pool;
+//  * plugin call (streaming): a sub-batch is also the unit that crosses PCIe on the copy stream while
+//    its predecessor is scored.  Byte schedule: a small first chunk (the kernels start early), full
+//    chunks, then a geometric tail s_k = shrink * s_{k-1}: the kernels are faster than the link, so as
+//    long as a chunk is not much smaller than its predecessor its copy hides the predecessor's kernels,
+//    and only the kernels of the LAST (smallest) chunk are exposed behind the end of the H2D stream.
+void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool streaming) {
+    e->chunks.clear();
+    e->chunks.push_back(0);
+    const int64_t n = e->n;
+    if (n <= 0) return;
+    const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
+    std::vector<size_t> target;
+    if (streaming) {
+        const size_t total = (size_t)hoff[n] * hit_row, full = e->chunk_bytes, first = full / 4;
+        std::vector<size_t> tail;
+        size_t acc = 0;
+        for (size_t t = std::max<size_t>(full / 6, size_t(1) << 20); e->chunk_shrink < 0.999 && t < full && acc + t + first < total;
+             t = (size_t)((double)t / e->chunk_shrink) + 1) {
+            tail.push_back(t);
+            acc += t;
+        }
+        size_t rem = total > acc ? total - acc : 0;
+        target.push_back(std::min(rem, first));
+        rem -= target.back();
+        if (rem % full) { target.push_back(rem % full); rem -= rem % full; }   // the odd piece goes early
+        for (; rem > 0; rem -= full) target.push_back(full);
+        target.insert(target.end(), tail.rbegin(), tail.rend());
+    }
+    int64_t c0 = 0;
+    size_t k = 0;
+    while (c0 < n) {
+        int64_t c1 = c0;
+        size_t est = 0;
+        const size_t goal = k < target.size() ? target[k] : e->chunk_bytes;
+        for (;;) {
+            // workspace estimate per contig (records + table + level arrays), see wfl_pipeline.cu
+            const size_t h = (size_t)(hoff[c1 + 1] - hoff[c1]), g = (size_t)(loff[c1 + 1] - loff[c1]);
+            est += 190 * h + 96 * g + 9000;
+            ++c1;
+            if (c1 >= n) break;
+            if (streaming && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > goal) break;
+            if (e->mode == 2 && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
+        }
+        e->chunks.push_back(c1);
+        c0 = c1;
+        ++k;
+    }
+}
+
+// All H2D copies of the plugin call, chunk by chunk on the copy stream, one event per chunk.
+int issue_chunk_copies(wfl_engine *e, const wfl_batch *src) {
+    const int64_t *hoff = src->hit_off, *loff = src->locus_off;
+    cudaStream_t cs = e->copy_stream;
+    for (size_t k = 0; k + 1 < e->chunks.size(); ++k) {
+        const int64_t c0 = e->chunks[k], c1 = e->chunks[k + 1];
+        const size_t h0 = (size_t)hoff[c0], h1 = (size_t)hoff[c1];
+        const size_t l0 = (size_t)loff[c0], l1 = (size_t)loff[c1];
+#define CP(dst, srcp, lo, hi)                                                                         \
+    if ((hi) > (lo))                                                                                  \
+    CU(cudaMemcpyAsync(const_cast<void *>(static_cast<const void *>((dst) + (lo))), (srcp) + (lo),    \
+                       ((hi) - (lo)) * sizeof(*(srcp)), cudaMemcpyHostToDevice, cs))
+        CP(e->b.hit_qstart, src->hit_qstart, h0, h1);
+        CP(e->b.hit_qend, src->hit_qend, h0, h1);
+        CP(e->b.hit_taxon, src->hit_taxon, h0, h1);
+        CP(e->b.hit_score, src->hit_score, h0, h1);
+        CP(e->b.hit_scov, src->hit_scov, h0, h1);
+        CP(e->b.hit_strand, src->hit_strand, h0, h1);
+        if (e->S > 0) CP(e->b.hit_sysmask, src->hit_sysmask, h0, h1);
+        CP(e->b.locus_start, src->locus_start, l0, l1);
+        CP(e->b.locus_end, src->locus_end, l0, l1);
+        CP(e->b.locus_strand, src->locus_strand, l0, l1);
+#undef CP
+        if (e->chunk_ev.size() <= k) {
+            cudaEvent_t evn;
+            CU(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
+            e->chunk_ev.push_back(evn);
+        }
+        CU(cudaEventRecord(e->chunk_ev[k], cs));
+    }
+    CU(cudaEventRecord(e->ev[5], cs));   // end of the last H2D chunk
+    e->chunks_streamed = true;
+    return WFL_OK;
+}
+
 // One sub-batch [c0, c1) through the multi-kernel pipeline (wfl_pipeline.cu).
-int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_t c1) {
+int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_t c1, int slot = 0) {
+    cudaStream_t stream = slot ? e->stream2 : e->stream;
     const int L = std::min(std::max(e->tax_max_depth + 1 - e->P.p.jump_taxonomy, 1), 64);
     int rc;
     char *pool;
@@ -280,16 +384,16 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     int *lists, *cnt;
     unsigned long long *wq;
     const size_t n = (size_t)e->n;
-    if ((rc = outbuf(e, e->pipe_pool, std::min<size_t>(e->pipe_pool_bytes, 200 * (size_t)e->nh + 9200 * n + 96 * (size_t)e->nl + (size_t(64) << 20)), &pool))) return rc;
+    if ((rc = outbuf(e, e->pipe_pool[slot], std::min<size_t>(e->pipe_pool_bytes, 200 * (size_t)e->nh + 9200 * n + 96 * (size_t)e->nl + (size_t(64) << 20)), &pool))) return rc;
     if ((rc = outbuf(e, e->pipe_ctg, n, &ctg))) return rc;
-    if ((rc = outbuf(e, e->pipe_lists, 3 * n + 16, &lists))) return rc;
-    if ((rc = outbuf(e, e->pipe_cnt, 2 * 66 + 8, &cnt))) return rc;
-    if ((rc = outbuf(e, e->pipe_wq, 3 * 66 + 8, &wq))) return rc;
-    CU(cudaMemsetAsync(cnt, 0, (2 * 66 + 8) * sizeof(int), e->stream));
-    CU(cudaMemsetAsync(wq, 0, (3 * 66 + 8) * sizeof(unsigned long long), e->stream));
+    if ((rc = outbuf(e, e->pipe_lists[slot], 3 * n + 16, &lists))) return rc;
+    if ((rc = outbuf(e, e->pipe_cnt[slot], 2 * 66 + 8, &cnt))) return rc;
+    if ((rc = outbuf(e, e->pipe_wq[slot], 3 * 66 + 8, &wq))) return rc;
+    CU(cudaMemsetAsync(cnt, 0, (2 * 66 + 8) * sizeof(int), stream));
+    CU(cudaMemsetAsync(wq, 0, (3 * 66 + 8) * sizeof(unsigned long long), stream));
     PipeArgs pa{};
     pa.b = sa.b; pa.t = sa.t; pa.o = sa.o; pa.P = sa.P; pa.ctr = sa.ctr;
-    pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool.cap;
+    pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool[slot].cap;
     pa.ctg = ctg;
     pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data; pa.plan_tree = sa.plan_tree;
     pa.dbg_contig = -1;
@@ -299,20 +403,20 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     pa.wq = wq + 1;
     pa.work_base = c0; pa.n_work = c1 - c0;
     pa.list_act = list[0]; pa.cnt_act = &cnt_act[0];
-    launch_pipe_prepare(pa, (int)std::min<int64_t>(grid, c1 - c0), e->stream);
+    launch_pipe_prepare(pa, (int)std::min<int64_t>(grid, c1 - c0), stream);
     for (int lvl = 0; lvl < L; ++lvl) {
         pa.list_act = list[lvl & 1]; pa.cnt_act = &cnt_act[lvl];
         pa.list_next = list[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
         pa.list_two = list[2]; pa.cnt_two = &cnt_two[lvl];
         pa.wq = wq + 2 + 3 * lvl;
-        launch_pipe_scores(pa, grid, e->stream);
+        launch_pipe_scores(pa, grid, stream);
         pa.wq = wq + 3 + 3 * lvl;
-        launch_pipe_one(pa, grid, e->stream);
+        launch_pipe_one(pa, grid, stream);
         pa.wq = wq + 4 + 3 * lvl;
-        launch_pipe_two(pa, grid, e->stream);
+        launch_pipe_two(pa, grid, stream);
     }
     pa.list_act = list[L & 1]; pa.cnt_act = &cnt_act[L];
-    launch_pipe_leftover(pa, e->stream);
+    launch_pipe_leftover(pa, stream);
     CU(cudaGetLastError());
     e->stats.kernel_launches += 2 + 3 * L;
     return WFL_OK;
@@ -383,53 +487,24 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
             // The batch is cut into chunks of contigs.  Plugin call (src != nullptr): chunk k+1 crosses
             // PCIe on the copy stream while chunk k is scored on the compute stream.  Pipeline mode: a
             // chunk is also the sub-batch whose intermediate state shares the workspace pool.
-            const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
-            const int64_t *hoff = e->h_hit_off.data(), *loff = e->h_locus_off.data();
-            int64_t c0 = 0;
-            size_t k = 0;
-            while (c0 < e->n) {
-                int64_t c1 = c0;
-                size_t est = 0;
-                for (;;) {
-                    // workspace estimate per contig (records + table + level arrays), see wfl_pipeline.cu
-                    const size_t h = (size_t)(hoff[c1 + 1] - hoff[c1]), g = (size_t)(loff[c1 + 1] - loff[c1]);
-                    est += 190 * h + 96 * g + 9000;
-                    ++c1;
-                    if (c1 >= e->n) break;
-                    // the first chunk is small so that the kernels start early; later ones amortise launches
-                    // the first chunk is small so that the kernels start early; later ones amortise launches
-                    if (src != nullptr && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > (k == 0 ? e->chunk_bytes / 4 : e->chunk_bytes)) break;
-                    if (e->mode == 2 && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
+            if (e->chunks.size() < 2 || e->chunks.back() != e->n)
+                plan_chunks(e, e->h_hit_off.data(), e->h_locus_off.data(), false);
+            bool used_slot1 = false;
+            for (size_t k = 0; k + 1 < e->chunks.size(); ++k) {
+                const int64_t c0 = e->chunks[k], c1 = e->chunks[k + 1];
+                // plugin call: sub-batches alternate between two compute streams, so the tail of one
+                // sub-batch's kernel chain (11+ dependent launches, each ending on its slowest contig)
+                // is filled by the next sub-batch's kernels instead of idling the SMs
+                const bool streamed = src != nullptr && e->chunks_streamed;
+                const int slot = (streamed && e->mode == 2 && e->n_slots > 1) ? (int)(k & 1) : 0;
+                if (slot && !used_slot1) {
+                    CU(cudaEventRecord(e->ev_join, e->stream));   // orders stream2 after the counter reset above
+                    CU(cudaStreamWaitEvent(e->stream2, e->ev_join, 0));
+                    used_slot1 = true;
                 }
-                if (src != nullptr) {
-                    const size_t h0 = (size_t)hoff[c0], h1 = (size_t)hoff[c1];
-                    const size_t l0 = (size_t)loff[c0], l1 = (size_t)loff[c1];
-                    cudaStream_t cs = e->copy_stream;
-#define CP(dst, srcp, lo, hi)                                                                         \
-    if ((hi) > (lo))                                                                                  \
-    CU(cudaMemcpyAsync(const_cast<void *>(static_cast<const void *>((dst) + (lo))), (srcp) + (lo),    \
-                       ((hi) - (lo)) * sizeof(*(srcp)), cudaMemcpyHostToDevice, cs))
-                    CP(e->b.hit_qstart, src->hit_qstart, h0, h1);
-                    CP(e->b.hit_qend, src->hit_qend, h0, h1);
-                    CP(e->b.hit_taxon, src->hit_taxon, h0, h1);
-                    CP(e->b.hit_score, src->hit_score, h0, h1);
-                    CP(e->b.hit_scov, src->hit_scov, h0, h1);
-                    CP(e->b.hit_strand, src->hit_strand, h0, h1);
-                    if (e->S > 0) CP(e->b.hit_sysmask, src->hit_sysmask, h0, h1);
-                    CP(e->b.locus_start, src->locus_start, l0, l1);
-                    CP(e->b.locus_end, src->locus_end, l0, l1);
-                    CP(e->b.locus_strand, src->locus_strand, l0, l1);
-#undef CP
-                    if (e->chunk_ev.size() <= k) {
-                        cudaEvent_t evn;
-                        CU(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
-                        e->chunk_ev.push_back(evn);
-                    }
-                    CU(cudaEventRecord(e->chunk_ev[k], cs));
-                    CU(cudaStreamWaitEvent(e->stream, e->chunk_ev[k], 0));
-                }
+                if (streamed) CU(cudaStreamWaitEvent(slot ? e->stream2 : e->stream, e->chunk_ev[k], 0));
                 if (e->mode == 2) {
-                    if ((rc = launch_pipeline_chunk(e, a, c0, c1))) return rc;
+                    if ((rc = launch_pipeline_chunk(e, a, c0, c1, slot))) return rc;
                 } else {
                     CU(cudaMemsetAsync(&ctr->next_work, 0, sizeof(unsigned long long), e->stream));
                     a.work_base = c0;
@@ -441,10 +516,11 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
                     CU(cudaGetLastError());
                     e->stats.kernel_launches++;
                 }
-                c0 = c1;
-                ++k;
             }
-            if (src != nullptr) CU(cudaEventRecord(e->ev[5], e->copy_stream));   // end of the last H2D chunk
+            if (used_slot1) {
+                CU(cudaEventRecord(e->ev_join, e->stream2));
+                CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+            }
         } else if (n_work > 0) {
             if (e->mode != 0)
                 launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, n_work), e->stream);
@@ -454,8 +530,10 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
             e->stats.kernel_launches++;
         }
         if (attempt == 0) CU(cudaEventRecord(e->ev[2], e->stream));
+        trace("kernels launched");
         CU(cudaMemcpyAsync(&hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
+        trace("kernels finished");
         acc = hc;
         if (hc.n_badinput) {
             set_err(e, "%llu contig(s) carry a hit taxon index outside the taxonomy", hc.n_badinput);
@@ -550,34 +628,18 @@ int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all) {
     b.n_hits = e->nh;
     b.n_loci = e->nl;
     const size_t n1 = (size_t)e->n + 1, nh = (size_t)e->nh, nl = (size_t)e->nl;
-    {
-        int maxlen = 0;
-        for (int64_t i = 0; i < in->n_loci; ++i) {
-            int d = in->locus_end[i] - in->locus_start[i];
-            d = (d < 0 ? -d : d) + 1;
-            maxlen = d > maxlen ? d : maxlen;
-        }
-        if ((rc = ensure_plan_table(e, maxlen))) return rc;
-    }
-    e->h_hit_off.assign(in->hit_off, in->hit_off + n1);
-    e->h_locus_off.assign(in->locus_off, in->locus_off + n1);
-    CU(cudaEventRecord(e->ev[0], e->stream));
-    if ((rc = upload(e, e->in[0], in->hit_off, n1, &b.hit_off))) return rc;
-    if ((rc = upload(e, e->in[1], in->locus_off, n1, &b.locus_off))) return rc;
-    if (copy_all) {
-        if ((rc = upload(e, e->in[2], in->hit_qstart, nh, &b.hit_qstart))) return rc;
-        if ((rc = upload(e, e->in[3], in->hit_qend, nh, &b.hit_qend))) return rc;
-        if ((rc = upload(e, e->in[4], in->hit_taxon, nh, &b.hit_taxon))) return rc;
-        if ((rc = upload(e, e->in[5], in->hit_score, nh, &b.hit_score))) return rc;
-        if ((rc = upload(e, e->in[6], in->hit_scov, nh, &b.hit_scov))) return rc;
-        if ((rc = upload(e, e->in[7], in->hit_strand, nh, &b.hit_strand))) return rc;
-        b.hit_sysmask = nullptr;
-        if (e->S > 0 && (rc = upload(e, e->in[8], in->hit_sysmask, nh, &b.hit_sysmask))) return rc;
-        if ((rc = upload(e, e->in[9], in->locus_start, nl, &b.locus_start))) return rc;
-        if ((rc = upload(e, e->in[10], in->locus_end, nl, &b.locus_end))) return rc;
-        if ((rc = upload(e, e->in[11], in->locus_strand, nl, &b.locus_strand))) return rc;
-    } else {
-        // device arrays only; run_kernels copies them chunk by chunk, overlapped with the kernels
+    e->chunks.clear();
+    e->chunks_streamed = false;
+    // The CSR offsets go first.  Plugin call: on the COPY stream, ahead of chunk 0 (two streams feeding the
+    // same DMA queue are not ordered by issue time: on the compute stream they ended up behind the whole
+    // bulk transfer and the first kernel with them); chunk 0's event covers them.
+    cudaStream_t os = copy_all ? e->stream : e->copy_stream;
+    CU(cudaEventRecord(e->ev[0], os));
+    if ((rc = upload(e, e->in[0], in->hit_off, n1, &b.hit_off, os))) return rc;
+    if ((rc = upload(e, e->in[1], in->locus_off, n1, &b.locus_off, os))) return rc;
+    if (!copy_all) {
+        // plugin call: device arrays only, and the chunked H2D copies start NOW on the copy stream -- the
+        // host-side preparation below (plan table, offsets) and the kernels overlap with the transfer
         rc = 0;
         rc |= outbuf(e, e->in[2], nh, const_cast<int32_t **>(&b.hit_qstart));
         rc |= outbuf(e, e->in[3], nh, const_cast<int32_t **>(&b.hit_qend));
@@ -591,10 +653,45 @@ int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all) {
         rc |= outbuf(e, e->in[10], nl, const_cast<int32_t **>(&b.locus_end));
         rc |= outbuf(e, e->in[11], nl, const_cast<int8_t **>(&b.locus_strand));
         if (rc) return WFL_ERR_CUDA;
+        if (e->n > 0) {
+            plan_chunks(e, in->hit_off, in->locus_off, true);
+            trace("chunks planned");
+            if ((rc = issue_chunk_copies(e, in))) return rc;
+            trace("chunk copies issued");
+        }
     }
-    CU(cudaEventRecord(e->ev[1], e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    CU(cudaEventElapsedTime(&e->stats.ms_h2d, e->ev[0], e->ev[1]));
+    {
+        int maxlen = 0;
+        for (int64_t i = 0; i < in->n_loci; ++i) {
+            int d = in->locus_end[i] - in->locus_start[i];
+            d = (d < 0 ? -d : d) + 1;
+            maxlen = d > maxlen ? d : maxlen;
+        }
+        if ((rc = ensure_plan_table(e, maxlen))) return rc;
+    }
+    e->h_hit_off.assign(in->hit_off, in->hit_off + n1);
+    e->h_locus_off.assign(in->locus_off, in->locus_off + n1);
+    if (copy_all) {
+        if ((rc = upload(e, e->in[2], in->hit_qstart, nh, &b.hit_qstart))) return rc;
+        if ((rc = upload(e, e->in[3], in->hit_qend, nh, &b.hit_qend))) return rc;
+        if ((rc = upload(e, e->in[4], in->hit_taxon, nh, &b.hit_taxon))) return rc;
+        if ((rc = upload(e, e->in[5], in->hit_score, nh, &b.hit_score))) return rc;
+        if ((rc = upload(e, e->in[6], in->hit_scov, nh, &b.hit_scov))) return rc;
+        if ((rc = upload(e, e->in[7], in->hit_strand, nh, &b.hit_strand))) return rc;
+        b.hit_sysmask = nullptr;
+        if (e->S > 0 && (rc = upload(e, e->in[8], in->hit_sysmask, nh, &b.hit_sysmask))) return rc;
+        if ((rc = upload(e, e->in[9], in->locus_start, nl, &b.locus_start))) return rc;
+        if ((rc = upload(e, e->in[10], in->locus_end, nl, &b.locus_end))) return rc;
+        if ((rc = upload(e, e->in[11], in->locus_strand, nl, &b.locus_strand))) return rc;
+    }
+    trace("host prep done");
+    if (copy_all) {
+        CU(cudaEventRecord(e->ev[1], e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaEventElapsedTime(&e->stats.ms_h2d, e->ev[0], e->ev[1]));
+    } else if (e->n == 0) {
+        CU(cudaStreamSynchronize(e->copy_stream));   // no chunk event will order the (empty) offsets
+    }
     e->have_batch = true;
     return WFL_OK;
 }
@@ -674,7 +771,9 @@ int wfl_create(int device, wfl_engine **out) {
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete e;
         return WFL_ERR_CUDA;
     }
@@ -687,6 +786,8 @@ int wfl_create(int device, wfl_engine **out) {
     if (const char *k = getenv("WFL_K2")) e->use_tree = std::string(k) == "tree";
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
     if (const char *k = getenv("WFL_CHUNK_MB")) e->chunk_bytes = (size_t)atoll(k) << 20;
+    if (const char *k = getenv("WFL_STREAMS")) e->n_slots = atoi(k) >= 2 ? 2 : 1;
+    if (const char *k = getenv("WFL_CHUNK_SHRINK")) e->chunk_shrink = std::min(1.0, std::max(0.05, atof(k)));
     e->smem_optin = prop.sharedMemPerBlockOptin;
     for (auto &ev : e->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) {
@@ -707,9 +808,12 @@ void wfl_destroy(wfl_engine *e) {
     for (auto &b : e->cm) fr(b);
     for (auto &b : e->dbg) fr(b);
     fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data); fr(e->plan_tree);
-    fr(e->pipe_pool); fr(e->pipe_ctg); fr(e->pipe_lists); fr(e->pipe_cnt); fr(e->pipe_wq);
+    for (int q = 0; q < 2; ++q) { fr(e->pipe_pool[q]); fr(e->pipe_lists[q]); fr(e->pipe_cnt[q]); fr(e->pipe_wq[q]); }
+    fr(e->pipe_ctg);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->chunk_ev) cudaEventDestroy(ev);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -804,12 +908,17 @@ int wfl_download_results(wfl_engine *e, wfl_results *out) {
 int wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out) {
     if (!e) return WFL_ERR_ARG;
     CU(cudaSetDevice(e->device));
+    trace("begin");
     int rc = stage_inputs(e, in, false);
     if (rc) return rc;
+    trace("inputs staged, copies in flight");
     if ((rc = run_kernels(e, in))) return rc;
+    trace("kernels + compaction done");
     float h2d = 0.f;
     if (e->n > 0 && cudaEventElapsedTime(&h2d, e->ev[0], e->ev[5]) == cudaSuccess) e->stats.ms_h2d = h2d;
-    return download(e, out);
+    rc = download(e, out);
+    trace("results downloaded");
+    return rc;
 }
 
 int wfl_host_alloc(size_t bytes, void **out) {
