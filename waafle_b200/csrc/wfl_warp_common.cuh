@@ -154,6 +154,7 @@ __device__ __noinline__ void warp_multisplit(int n, int nbins, const int *key, c
 // The split tree depends only on n, so it is flattened once per locus into a leaf plan shared by
 // all clades: plan entry = leaf size m | (#pending left sums to add after this leaf) << 8.
 
+// K2-HOST-BEGIN (tests/test_k2_host.py compiles everything up to K2-HOST-END for the host)
 // Emit the leaf plan of an n-element sum (at most plan_cap(n) entries).  Every leaf of a split
 // node has more than 56 elements, hence the bound.
 __device__ __forceinline__ int plan_cap(int n) { return n / 57 + 2; }
@@ -547,6 +548,8 @@ __device__ __noinline__ double group_mean(const int *ra, const int *rb, const do
     }
     return st[0] / (double)n;
 }
+
+// K2-HOST-END
 
 // Generic sequential pairwise sum for the short gene-level vectors of Contig.score.
 template <class Src>
