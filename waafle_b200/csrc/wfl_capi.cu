@@ -56,6 +56,8 @@ struct wfl_engine {
     std::vector<int64_t> h_hit_off, h_locus_off;
     std::vector<int64_t> chunks;         // contig boundaries of the sub-batches of the current batch
     bool chunks_streamed = false;        // their H2D copies are in flight on copy_stream (plugin call)
+    int resident_split = 1;              // WFL_SPLIT > 1: sub-batches of a resident batch on both compute streams (measured
+                                         // slower: kernels of different phases then share the SMs and their instruction caches)
     double chunk_shrink = 1.0;           // < 1: geometric tail of the streaming schedule, each chunk >= shrink * its
                                          // predecessor (WFL_CHUNK_SHRINK; measured no better than equal chunks)
     wfl_stats stats{};
@@ -318,6 +320,11 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
         for (; rem > 0; rem -= full) target.push_back(full);
         target.insert(target.end(), tail.rbegin(), tail.rend());
     }
+    // resident batch (pipeline mode): a few sub-batches alternating between the two compute streams, so that
+    // the tail of one sub-batch's kernel chain is filled by the other's kernels
+    size_t split_hits = 0;
+    if (!streaming && e->mode == 2 && e->n_slots > 1 && e->resident_split > 1 && n >= 8192 * (int64_t)e->resident_split)
+        split_hits = (size_t)hoff[n] / (size_t)e->resident_split + 1;
     int64_t c0 = 0;
     size_t k = 0;
     while (c0 < n) {
@@ -331,6 +338,7 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
             ++c1;
             if (c1 >= n) break;
             if (streaming && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > goal) break;
+            if (!streaming && split_hits && (size_t)(hoff[c1 + 1] - hoff[c0]) > split_hits) break;
             if (e->mode == 2 && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
         }
         e->chunks.push_back(c1);
@@ -496,7 +504,7 @@ int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
                 // sub-batch's kernel chain (11+ dependent launches, each ending on its slowest contig)
                 // is filled by the next sub-batch's kernels instead of idling the SMs
                 const bool streamed = src != nullptr && e->chunks_streamed;
-                const int slot = (streamed && e->mode == 2 && e->n_slots > 1) ? (int)(k & 1) : 0;
+                const int slot = (e->mode == 2 && e->n_slots > 1 && e->chunks.size() > 2) ? (int)(k & 1) : 0;
                 if (slot && !used_slot1) {
                     CU(cudaEventRecord(e->ev_join, e->stream));   // orders stream2 after the counter reset above
                     CU(cudaStreamWaitEvent(e->stream2, e->ev_join, 0));
@@ -786,6 +794,7 @@ int wfl_create(int device, wfl_engine **out) {
     if (const char *k = getenv("WFL_K2")) e->use_tree = std::string(k) == "tree";
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
     if (const char *k = getenv("WFL_CHUNK_MB")) e->chunk_bytes = (size_t)atoll(k) << 20;
+    if (const char *k = getenv("WFL_SPLIT")) e->resident_split = std::max(1, atoi(k));
     if (const char *k = getenv("WFL_STREAMS")) e->n_slots = atoi(k) >= 2 ? 2 : 1;
     if (const char *k = getenv("WFL_CHUNK_SHRINK")) e->chunk_shrink = std::min(1.0, std::max(0.05, atof(k)));
     e->smem_optin = prop.sharedMemPerBlockOptin;

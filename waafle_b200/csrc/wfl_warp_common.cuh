@@ -289,13 +289,45 @@ __device__ __forceinline__ double const_leaf(Site &s, int m) {
     return res;
 }
 
-// A leaf that contains envelope breakpoints.
-__device__ __forceinline__ double mixed_leaf(Site &s, int m) {
-    const int p0 = s.pos;
+// COLD path, kept out of line so that the hot leaf code stays compact in the instruction cache: a leaf of
+// a gene shorter than 8 sites, or a leaf with more than RMAX runs -- literal per-site evaluation.
+__device__ __noinline__ double literal_leaf(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
+                                            bool sorted, int p0, int m) {
+    Site s;
+    s.ra = ra; s.rb = rb; s.rv = rv;
+    s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
+    s.k8[0] = s.k8[1] = s.k8[2] = s.k8[3] = 0;
+    s.memo_ok = false;
+    s.pos = p0;
+    s.run_end = p0;
+    s.run_v = 0.0;
     if (m < 8) {
         double r = 0.0;
 #pragma unroll 1
         for (int i = 0; i < m; ++i) r += s.next();
+        return r;
+    }
+    const int k8 = m >> 3, body = k8 << 3;
+    double r[8];
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) r[j] = s.next();
+#pragma unroll 1
+    for (int c = 1; c < k8; ++c) {
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) r[j] += s.next();
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll 1
+    for (int p = body; p < m; ++p) res += s.next();
+    return res;
+}
+
+// A leaf that contains envelope breakpoints.
+__device__ __forceinline__ double mixed_leaf(Site &s, int m) {
+    const int p0 = s.pos;
+    if (m < 8) {
+        const double r = literal_leaf(s.ra, s.rb, s.rv, s.rs, s.re, s.n, s.sorted, p0, m);
+        s.pos = s.run_end = p0 + m;   // the next leaf re-reads its run
         return r;
     }
     // collect the runs that intersect the leaf (ends relative to the leaf start)
@@ -407,19 +439,8 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
         return res;
     }
     // more than RMAX runs in one leaf: literal per-site evaluation
-    s.pos = p0;
-    s.run_end = p0;
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = s.next();
-#pragma unroll 1
-    for (int c = 1; c < k8; ++c) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += s.next();
-    }
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-#pragma unroll 1
-    for (int p = body; p < m; ++p) res += s.next();
+    const double res = literal_leaf(s.ra, s.rb, s.rv, s.rs, s.re, s.n, s.sorted, p0, m);
+    s.pos = s.run_end = p0 + m;   // the next leaf re-reads its run
     return res;
 }
 
