@@ -96,16 +96,18 @@ LEVEL_BLOCKS = dict(F=F, G2=G2, H=H, I=I, J=J, K=K, L2=L2, Mm=Mm, N=N)
 
 TEMPLATE = r'''// GENERATED by tools/gen_pipeline.py from wfl_score_warp.cu -- do not edit by hand.
 //
-// The orgscorer path as a pipeline of four small kernels (same per-phase code as the monolithic
+// The orgscorer path as a pipeline of six small kernels (same per-phase code as the monolithic
 // warp-per-contig kernel, one warp per contig in every kernel):
 //
 //   wfl_pipe_prepare : K1 match + record emission, K3 annotations, base order, distinct-clade table
 //                      (the only kernel that streams the hit SoA from HBM)
-//   wfl_pipe_scores  : K5 regroup, K2 envelope integrals, K4 weak loci, clade rows + gene bitmasks
+//   wfl_pipe_regroup : K5 regroup (stable multisplit by clade rank, group table)
+//   wfl_pipe_scores  : K2 envelope integrals (gene score per (clade, locus) group)
+//   wfl_pipe_masks   : K4 weak loci, clade rows + gene bitmasks
 //   wfl_pipe_one     : K6 one-clade search + meld; unresolved contigs go to the two-clade list
 //   wfl_pipe_two     : K7/K8 two-clade search, meld, LGT filters; K9 stop-or-lift (next level's list)
 //
-// scores/one/two are launched once per taxonomy level over device-side work lists (no host sync in
+// regroup/scores/masks/one/two are launched once per taxonomy level over device-side work lists (no host sync in
 // the level loop; an empty list makes the launch a no-op).  Between kernels a contig's state lives
 // in a global workspace pool (regions A: loci, B: records + clade table, C: per-level arrays), carved
 // by the same deterministic bump arena in every kernel.  Why: the monolithic kernel is bound by
@@ -384,9 +386,12 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 2: regroup + gene scores + weak loci + masks (one taxonomy level)
+// kernel 2a: regroup (K5) -- records in (clade, locus) group order, group table
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeArgs a) {
+// The scoring step is cut in three kernels (regroup | K2 | masks) for the same reason the pipeline
+// exists: as one kernel it ran with an SM instruction-cache hit rate of 87 % and the GPC instruction
+// cache at 92 % of its request throughput (profiles/r1_final2_pipeline_kernels_ncu.txt).
+__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_regroup(const PipeArgs a) {
     const int lane = threadIdx.x;
     const DevParams &P = a.P;
     const DevTax &tax = a.t;
@@ -399,38 +404,91 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeA
         const long long t_start = clock64();
         OPEN_CONTIG
         RESULT_LOCALS
-        bool overflow = false, cont_ok = false;
-        int Ngrp = 0, ng = 0, nlt = 0, nu = 0, t_unk = -1, nun = 0, hasroot = 0;
-        long long n_groups = 0, t_f = 0, t_g = 0;
+        bool overflow = false;
+        int Ngrp = 0, ng = 0, nlt = 0, nu = 0, t_unk = -1;
+        long long n_groups = 0;
 #pragma unroll 1
         for (int once = 0; once < 1; ++once) {
 @F@
-            t_f = clock64();
-@G2@
-            t_g = clock64();
-@H@
-@I@
-            cont_ok = true;
         }
         if (lane == 0) {
             atomicAdd(&a.ctr->groups, (unsigned long long)n_groups);
             atomicAdd(&a.ctr->levels, 1ull);
-            const long long t_end = clock64();
-            if (t_g) {   // sub-phases: regroup + group table | K2 envelope integrals | weak loci + masks
-                atomicAdd(&a.ctr->phase_cycles[2], (unsigned long long)(t_f - t_start));
-                atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(t_g - t_f));
-                atomicAdd(&a.ctr->phase_cycles[4], (unsigned long long)(t_end - t_g));
-            } else {
-                atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(t_end - t_start));
-            }
+            atomicAdd(&a.ctr->phase_cycles[2], (unsigned long long)(clock64() - t_start));
         }
+        if (overflow) {
+            EMIT_RESULT(1);
+        } else if (lane == 0) {
+            PipeCtg *cp = &a.ctg[c];
+            cp->Ngrp = Ngrp; cp->ng = ng; cp->nlt = nlt; cp->nu = nu; cp->t_unk = t_unk;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2b: K2 -- envelope integral of every (clade, locus) group, numpy-pairwise-exact
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeArgs a) {
+    const int lane = threadIdx.x;
+    const DevParams &P = a.P;
+    const DevTax &tax = a.t;
+    const int S = P.p.n_systems;
+#pragma unroll 1
+    for (;;) {
+        const long long c = pop_work(a.wq, a.list_act, a.cnt_act, lane);
+        if (c < 0) break;
+        if (a.ctg[c].state != PIPE_ACTIVE) continue;
+        const long long t_start = clock64();
+        OPEN_CONTIG
+        const int Ngrp = cx.Ngrp, ng = cx.ng;
+        DECL_CUR
+        DECL_GROUPS
+        (void)cur; (void)gs; (void)T; (void)lifts; (void)l_raw; (void)l0; (void)ign; (void)um; (void)r_t; (void)r_loc;
+@G2@
+        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(clock64() - t_start));
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2c: weak loci (K4), clade rows and gene bitmasks
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_masks(const PipeArgs a) {
+    const int lane = threadIdx.x;
+    const DevParams &P = a.P;
+    const DevTax &tax = a.t;
+    const int S = P.p.n_systems;
+    const bool spike = P.p.weak_loci == 2;
+#pragma unroll 1
+    for (;;) {
+        const long long c = pop_work(a.wq, a.list_act, a.cnt_act, lane);
+        if (c < 0) break;
+        if (a.ctg[c].state != PIPE_ACTIVE) continue;
+        const long long t_start = clock64();
+        OPEN_CONTIG
+        RESULT_LOCALS
+        const int Ngrp = cx.Ngrp, ng = cx.ng, nlt = cx.nlt;
+        DECL_CUR
+        DECL_GROUPS
+        (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_rs; (void)g_re; (void)gs; (void)g_perm; (void)gcur;
+        (void)r_t; (void)r_loc;
+        bool overflow = false, cont_ok = false;
+        int nun = 0, hasroot = 0;
+#pragma unroll 1
+        for (int once = 0; once < 1; ++once) {
+@H@
+@I@
+            cont_ok = true;
+        }
+        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[4], (unsigned long long)(clock64() - t_start));
         if (overflow) {
             EMIT_RESULT(1);
         } else if (!cont_ok) {
             EMIT_RESULT(0);   // "empty" contig: every locus ignored at the first level (unclassified)
         } else if (lane == 0) {
             PipeCtg *cp = &a.ctg[c];
-            cp->Ngrp = Ngrp; cp->ng = ng; cp->nlt = nlt; cp->nu = nu; cp->t_unk = t_unk; cp->nun = nun;
+            cp->nun = nun;
             cp->hasroot = hasroot;
         }
         __syncwarp();
@@ -550,7 +608,9 @@ __global__ void wfl_pipe_leftover(const PipeArgs a) {
 // host side: launch sequence for one sub-batch
 // ---------------------------------------------------------------------------------------------
 void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_prepare<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_regroup<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_scores<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_masks<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_one<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_two<<<grid, 32, 0, s>>>(a); }
 int pipe_ctas_per_sm() { return WFL_PIPE_CPSM; }

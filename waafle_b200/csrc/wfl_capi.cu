@@ -396,9 +396,9 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     if ((rc = outbuf(e, e->pipe_ctg, n, &ctg))) return rc;
     if ((rc = outbuf(e, e->pipe_lists[slot], 3 * n + 16, &lists))) return rc;
     if ((rc = outbuf(e, e->pipe_cnt[slot], 2 * 66 + 8, &cnt))) return rc;
-    if ((rc = outbuf(e, e->pipe_wq[slot], 3 * 66 + 8, &wq))) return rc;
+    if ((rc = outbuf(e, e->pipe_wq[slot], 5 * 66 + 8, &wq))) return rc;
     CU(cudaMemsetAsync(cnt, 0, (2 * 66 + 8) * sizeof(int), stream));
-    CU(cudaMemsetAsync(wq, 0, (3 * 66 + 8) * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(wq, 0, (5 * 66 + 8) * sizeof(unsigned long long), stream));
     PipeArgs pa{};
     pa.b = sa.b; pa.t = sa.t; pa.o = sa.o; pa.P = sa.P; pa.ctr = sa.ctr;
     pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool[slot].cap;
@@ -416,17 +416,21 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
         pa.list_act = list[lvl & 1]; pa.cnt_act = &cnt_act[lvl];
         pa.list_next = list[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
         pa.list_two = list[2]; pa.cnt_two = &cnt_two[lvl];
-        pa.wq = wq + 2 + 3 * lvl;
+        pa.wq = wq + 2 + 5 * lvl;
+        launch_pipe_regroup(pa, grid, stream);
+        pa.wq = wq + 3 + 5 * lvl;
         launch_pipe_scores(pa, grid, stream);
-        pa.wq = wq + 3 + 3 * lvl;
+        pa.wq = wq + 4 + 5 * lvl;
+        launch_pipe_masks(pa, grid, stream);
+        pa.wq = wq + 5 + 5 * lvl;
         launch_pipe_one(pa, grid, stream);
-        pa.wq = wq + 4 + 3 * lvl;
+        pa.wq = wq + 6 + 5 * lvl;
         launch_pipe_two(pa, grid, stream);
     }
     pa.list_act = list[L & 1]; pa.cnt_act = &cnt_act[L];
     launch_pipe_leftover(pa, stream);
     CU(cudaGetLastError());
-    e->stats.kernel_launches += 2 + 3 * L;
+    e->stats.kernel_launches += 2 + 5 * L;
     return WFL_OK;
 }
 

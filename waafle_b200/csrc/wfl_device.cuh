@@ -147,7 +147,9 @@ struct PipeArgs {
 };
 
 void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_leftover(const PipeArgs &a, cudaStream_t s);
