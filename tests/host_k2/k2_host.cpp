@@ -22,6 +22,9 @@ using std::max;
 using std::min;
 constexpr int MAXDEPTH = 28;
 constexpr int RMAX = 6;
+#define WFL_K2_TREE 1
+#define WFL_K2_TWO 1
+#define WFL_K2_CONV 0
 struct TreeEntry { uint16_t size; uint8_t li, ri; };
 
 #include "k2_region.inc"

@@ -517,6 +517,37 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                         warp_multisplit(Ngrp, 2 * G, gkey, nullptr, gcur, g_perm);
                     }
                     __syncwarp();
+#if WFL_K2_CONV
+#pragma unroll 1
+                    for (int base = 0; base < Ngrp; base += 32) {
+                        // all 32 lanes call group_mean_warp together (it re-converges them before every leaf)
+                        const int gi = base + lane;
+                        int g = 0, rs = -1, re = 0, t = 0, loc = 0, nleaf = 0;
+                        if (gi < Ngrp) {
+                            g = g_perm[gi];
+                            rs = g_rs[g];
+                            if (rs >= 0) {
+                                t = g_t[g];
+                                loc = g_loc[g];
+                                re = g_re[g];
+                                nleaf = l_nleaf[loc];
+                            }
+                        }
+                        double sc;
+                        if (a.plan_tree != nullptr) {   // experimental tree walk: per lane
+                            sc = rs >= 0 ? group_mean(s_a, s_b, s_v, rs, re, l_len[loc], have_base_ord, l_k8[loc],
+                                                      l_plan[loc], nleaf) : 0.0;
+                        } else {
+                            sc = group_mean_warp(s_a, s_b, s_v, max(rs, 0), re, l_len[loc], have_base_ord, l_k8[loc],
+                                                 l_plan[loc], rs >= 0 ? nleaf : 0);
+                        }
+                        if (rs >= 0) {
+                            g_score[g] = sc;
+                            if (cl_id[t] != tax.unknown)   // waafle_orgscorer.py:409-411
+                                atomicMax(&maxb[loc], dbits(sc));
+                        }
+                    }
+#else
 #pragma unroll 1
                     for (int base = 0; base < Ngrp; base += 32) {
                         int gi = base + lane;
@@ -534,6 +565,7 @@ __global__ void __launch_bounds__(32) wfl_score_contigs_warp(const ScoreArgs a) 
                             }
                         }
                     }
+#endif
                     __syncwarp();
                     PH(3);
                     // ---- K4: weak loci (waafle_orgscorer.py:412-427) ---------------------------------

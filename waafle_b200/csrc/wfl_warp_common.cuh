@@ -15,6 +15,15 @@ typedef unsigned char u8;
 constexpr u32 FULL = 0xffffffffu;
 constexpr int MAXDEPTH = 28;   // pairwise tree depth for n < 2^31
 constexpr int BITMAP_MAX_WORDS = 1024;   // taxonomies up to 32768 nodes use the bitmap clade table
+#ifndef WFL_K2_TWO
+#define WFL_K2_TWO 1     // closed form for leaves with two run boundaries
+#endif
+#ifndef WFL_K2_CONV
+#define WFL_K2_CONV 0    // all lanes walk the leaf plan together, convergence barrier before every leaf
+#endif
+#ifndef WFL_K2_TREE
+#define WFL_K2_TREE 1    // experimental tree walk (WFL_K2=tree) compiled in
+#endif
 constexpr int RMAX = 6;        // envelope runs handled per mixed leaf before the per-site fallback
 
 // Order-preserving map double -> u64 (max on the bits == max on the doubles).
@@ -386,6 +395,48 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
         s.pos = p0 + m;
         return res;
     }
+#if WFL_K2_TWO
+    if (nr == 3 && rend[0] < body) {
+        // TWO boundaries b1 < b2 (typically a lower-scoring hit sticking out of the best one next to the
+        // zero flank): column j holds n0(j) copies of v0, then v1 up to n01(j), then v2, with
+        // n0(j) = (b1 >> 3) + (j < (b1 & 7)) and n01(j) = min(k8, (b2 >> 3) + (j < (b2 & 7))) -- at most three
+        // distinct columns, split at t1 <= t2.  All state in registers.
+        const int b1 = rend[0], b2 = rend[1];
+        const double v0 = rval[0], v1 = rval[1], v2 = rval[2];
+        const int J1 = b1 & 7, J2 = (b2 >> 3) < k8 ? (b2 & 7) : 0;
+        const int t1 = min(J1, J2), t2 = max(J1, J2);
+        double xa = 0.0, xb = 0.0, xc = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+            const int j = q == 0 ? 0 : (q == 1 ? t1 : t2);
+            if ((q == 0 && t1 == 0) || (q == 1 && t2 == t1)) continue;   // empty class
+            const int n0 = (b1 >> 3) + (j < J1), n01 = min(k8, (b2 >> 3) + (j < (b2 & 7)));
+            double acc = 0.0;   // 0 + v == v: the first term needs no special case
+            if (v0 != 0.0) {
+#pragma unroll 1
+                for (int i = 0; i < n0; ++i) acc += v0;
+            }
+            if (v1 != 0.0) {
+#pragma unroll 1
+                for (int i = n0; i < n01; ++i) acc += v1;
+            }
+            if (v2 != 0.0) {
+#pragma unroll 1
+                for (int i = n01; i < k8; ++i) acc += v2;
+            }
+            if (q == 0) xa = acc; else if (q == 1) xb = acc; else xc = acc;
+        }
+        const double r0 = 0 < t1 ? xa : (0 < t2 ? xb : xc), r1 = 1 < t1 ? xa : (1 < t2 ? xb : xc);
+        const double r2 = 2 < t1 ? xa : (2 < t2 ? xb : xc), r3 = 3 < t1 ? xa : (3 < t2 ? xb : xc);
+        const double r4 = 4 < t1 ? xa : (4 < t2 ? xb : xc), r5 = 5 < t1 ? xa : (5 < t2 ? xb : xc);
+        const double r6 = 6 < t1 ? xa : (6 < t2 ? xb : xc);
+        double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + xc));
+#pragma unroll 1
+        for (int p = body; p < m; ++p) res += p < b2 ? v1 : v2;   // the n % 8 tail lies behind b1
+        s.pos = p0 + m;
+        return res;
+    }
+#endif
     if (nr > 0) {
         // column j accumulates a[j], a[8+j], ...: runs enter it as (count, value) stretches;
         // neighbouring columns differ only where a run boundary b has b % 8 == j.  The eight
@@ -444,6 +495,7 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
     return res;
 }
 
+#if WFL_K2_TREE
 // Tree walk of the same sum.  numpy's split depends only on the node size, so the tree of an n-element
 // sum has a handful of distinct node sizes (<= 23 for n <= 16384; host-built table, children by index).
 // A node that lies inside ONE envelope run is a sum over a constant array: its value C(size, v) is
@@ -543,12 +595,16 @@ __device__ __noinline__ double group_mean_tree(const int *ra, const int *rb, con
     return ret / (double)n;
 }
 
+#endif
+
 // np.mean of the group's site array (waafle_orgscorer.py:403) without materialising it.
 // ra/rb/rv[rs..re) are the group's records (in descending score order if `sorted`).
 __device__ __noinline__ double group_mean(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
                                           bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
+#if WFL_K2_TREE
     if (nleaf < 0)   // tree mode: `plan` is the node-size table of this gene length
         return group_mean_tree(ra, rb, rv, rs, re, n, sorted, reinterpret_cast<const TreeEntry *>(plan), -nleaf);
+#endif
     Site s;
     s.ra = ra; s.rb = rb; s.rv = rv;
     s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
@@ -569,6 +625,38 @@ __device__ __noinline__ double group_mean(const int *ra, const int *rb, const do
     }
     return st[0] / (double)n;
 }
+
+#if WFL_K2_CONV
+// The same sum, called by ALL 32 lanes of a warp at once (a lane without a group passes nleaf = 0); the lanes
+// meet at a convergence barrier before every leaf.
+__device__ __noinline__ double group_mean_warp(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
+                                               bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
+    Site s;
+    s.ra = ra; s.rb = rb; s.rv = rv;
+    s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
+    s.k8[0] = (u8)k8pack; s.k8[1] = (u8)(k8pack >> 8); s.k8[2] = (u8)(k8pack >> 16); s.k8[3] = (u8)(k8pack >> 24);
+    s.pos = 0;
+    s.run_end = 0;
+    s.memo_ok = false;
+    double st[MAXDEPTH];
+    int sp = 0;
+    st[0] = 0.0;
+    const int nmax = __reduce_max_sync(0xffffffffu, nleaf);
+#pragma unroll 1
+    for (int l = 0; l < nmax; ++l) {
+        __syncwarp();
+        if (l < nleaf) {
+            const int e = plan[l], m = e & 0xff, nadd = e >> 8;
+            if (s.pos >= s.run_end) s.advance();
+            double val = (s.run_end - s.pos >= m) ? const_leaf(s, m) : mixed_leaf(s, m);
+#pragma unroll 1
+            for (int q = 0; q < nadd; ++q) val = st[--sp] + val;
+            st[sp++] = val;
+        }
+    }
+    return st[0] / (double)n;
+}
+#endif
 
 // K2-HOST-END
 
