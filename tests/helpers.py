@@ -202,6 +202,12 @@ def adversarial_batches():
              hits=[(1, 1000, "s__A", 0.45, 1.0, "+"), (1200, 2200, "s__A", 0.3, 1.0, "+")]),
         dict(loci=[(1, 1000, "+"), (1200, 2200, "+")],
              hits=[(1, 1000, "s__novel1", 0.95, 1.0, "+"), (1200, 2200, "s__novel2", 0.95, 1.0, "+")]),
+        # scores the front end never produces but the ABI accepts: -0.0 and negative (the engine's integer
+        # ranking of score bit patterns must fall back to floating-point compares for this contig)
+        dict(loci=[(1, 1000, "+"), (1200, 2200, "+")],
+             hits=[(1, 1000, "s__A", 0.9, 1.0, "+"), (1, 900, "s__A", -0.0, 1.0, "+"), (50, 1000, "s__A", -0.25, 1.0, "+"),
+                   (1200, 2200, "s__A", 0.7, 1.0, "+"), (1200, 2100, "s__B", -0.0, 1.0, "+"),
+                   (1250, 2200, "s__B", 0.0, 1.0, "+"), (1200, 2200, "s__D", 0.7, 1.0, "+")]),
     ]
     out["odd_inputs"] = make_batch(cs, TAX8)
     return out
