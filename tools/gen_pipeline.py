@@ -96,7 +96,7 @@ LEVEL_BLOCKS = dict(F=F, G2=G2, H=H, I=I, J=J, K=K, L2=L2, Mm=Mm, N=N)
 
 TEMPLATE = r'''// GENERATED by tools/gen_pipeline.py from wfl_score_warp.cu -- do not edit by hand.
 //
-// The orgscorer path as a pipeline of six small kernels (same per-phase code as the monolithic
+// The orgscorer path as a pipeline of seven small kernels (same per-phase code as the monolithic
 // warp-per-contig kernel, one warp per contig in every kernel):
 //
 //   wfl_pipe_prepare : K1 match + record emission, K3 annotations, base order, distinct-clade table
@@ -105,9 +105,10 @@ TEMPLATE = r'''// GENERATED by tools/gen_pipeline.py from wfl_score_warp.cu -- d
 //   wfl_pipe_scores  : K2 envelope integrals (gene score per (clade, locus) group)
 //   wfl_pipe_masks   : K4 weak loci, clade rows + gene bitmasks
 //   wfl_pipe_one     : K6 one-clade search + meld; unresolved contigs go to the two-clade list
-//   wfl_pipe_two     : K7/K8 two-clade search, meld, LGT filters; K9 stop-or-lift (next level's list)
+//   wfl_pipe_two     : K7/K8 two-clade search, meld, LGT filters; undecided contigs go to the lift list
+//   wfl_pipe_lift    : K9 stop-or-lift (K5 lift of the clade table; next level's list)
 //
-// regroup/scores/masks/one/two are launched once per taxonomy level over device-side work lists (no host sync in
+// regroup/scores/masks/one/two/lift are launched once per taxonomy level over device-side work lists (no host sync in
 // the level loop; an empty list makes the launch a no-op).  Between kernels a contig's state lives
 // in a global workspace pool (regions A: loci, B: records + clade table, C: per-level arrays), carved
 // by the same deterministic bump arena in every kernel.  Why: the monolithic kernel is bound by
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_one(const PipeArgs
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 4: two-clade search, decision, stop-or-lift
+// kernel 4a: two-clade search and decision; undecided contigs go to the lift list
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs a) {
     const int lane = threadIdx.x;
@@ -555,8 +556,9 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
         DECL_CLADES
         (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
         (void)cl_rank; (void)cl_crit; (void)cl_opt; (void)mk0; (void)mk2; (void)cl_go; (void)cl_par;
+        (void)nu; (void)t_unk; (void)hasroot; (void)spike; (void)T; (void)r_t; (void)r_loc;
         const Level &L = *Lp;
-        bool overflow = false, lifted = false;
+        bool overflow = false, undecided = false;
         unsigned long long need_hint = 0;
         (void)need_hint;
         long long n_ptest = 0, n_pscore = 0;
@@ -564,14 +566,57 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
         for (int once = 0; once < 1; ++once) {
 @L2@
 @Mm@
-@N@
-            lifted = true;
+            undecided = true;
         }
         if (lane == 0) {
             if (n_ptest) atomicAdd(&a.ctr->pairs_tested, (unsigned long long)n_ptest);
             if (n_pscore) atomicAdd(&a.ctr->pairs_scored, (unsigned long long)n_pscore);
             atomicAdd(&a.ctr->phase_cycles[6], (unsigned long long)(clock64() - t_start));
         }
+        if (overflow) {
+            r_call = WFL_CALL_UNCLASSIFIED;
+            r_na = r_nb = 0;
+            EMIT_RESULT(1);
+        } else if (!undecided) {
+            EMIT_RESULT(r_status);
+        } else if (lane == 0) {
+            int slot = atomicAdd(a.cnt_lift, 1);
+            a.list_lift[slot] = (int)c;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 4b: stop (root reached / nothing left) or lift the clade table to the parents (K9, K5)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_lift(const PipeArgs a) {
+    const int lane = threadIdx.x;
+    const DevParams &P = a.P;
+    const DevTax &tax = a.t;
+    const int S = P.p.n_systems;
+    const bool spike = P.p.weak_loci == 2;
+#pragma unroll 1
+    for (;;) {
+        const long long c = pop_work(a.wq, a.list_lift, a.cnt_lift, lane);
+        if (c < 0) break;
+        const long long t_start = clock64();
+        OPEN_CONTIG
+        RESULT_LOCALS
+        const int Ngrp = cx.Ngrp, ng = cx.ng, nu = cx.nu, t_unk = cx.t_unk, hasroot = cx.hasroot;
+        DECL_CUR
+        DECL_GROUPS
+        DECL_CLADES
+        (void)cur; (void)s_a; (void)s_b; (void)s_v; (void)g_score; (void)g_rs; (void)g_re; (void)g_loc; (void)g_t; (void)gs; (void)g_perm; (void)gcur;
+        (void)cl_rank; (void)cl_crit; (void)cl_opt; (void)mk0; (void)mk1; (void)mk2; (void)cl_go; (void)cl_par; (void)cand;
+        (void)memA; (void)memB; (void)bestm; (void)Lp; (void)nu; (void)t_unk; (void)r_loc; (void)l_raw; (void)l0; (void)ign; (void)um;
+        bool overflow = false, lifted = false;
+#pragma unroll 1
+        for (int once = 0; once < 1; ++once) {
+@N@
+            lifted = true;
+        }
+        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[7], (unsigned long long)(clock64() - t_start));
         if (overflow) {
             r_call = WFL_CALL_UNCLASSIFIED;
             r_na = r_nb = 0;
@@ -613,6 +658,7 @@ void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_
 void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_masks<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_one<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_two<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_lift(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_lift<<<grid, 32, 0, s>>>(a); }
 int pipe_ctas_per_sm() { return WFL_PIPE_CPSM; }
 void launch_pipe_leftover(const PipeArgs &a, cudaStream_t s) { wfl_pipe_leftover<<<64, 256, 0, s>>>(a); }
 

@@ -394,19 +394,19 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     const size_t n = (size_t)e->n;
     if ((rc = outbuf(e, e->pipe_pool[slot], std::min<size_t>(e->pipe_pool_bytes, 200 * (size_t)e->nh + 9200 * n + 96 * (size_t)e->nl + (size_t(64) << 20)), &pool))) return rc;
     if ((rc = outbuf(e, e->pipe_ctg, n, &ctg))) return rc;
-    if ((rc = outbuf(e, e->pipe_lists[slot], 3 * n + 16, &lists))) return rc;
-    if ((rc = outbuf(e, e->pipe_cnt[slot], 2 * 66 + 8, &cnt))) return rc;
-    if ((rc = outbuf(e, e->pipe_wq[slot], 5 * 66 + 8, &wq))) return rc;
-    CU(cudaMemsetAsync(cnt, 0, (2 * 66 + 8) * sizeof(int), stream));
-    CU(cudaMemsetAsync(wq, 0, (5 * 66 + 8) * sizeof(unsigned long long), stream));
+    if ((rc = outbuf(e, e->pipe_lists[slot], 4 * n + 16, &lists))) return rc;
+    if ((rc = outbuf(e, e->pipe_cnt[slot], 3 * 66 + 8, &cnt))) return rc;
+    if ((rc = outbuf(e, e->pipe_wq[slot], 6 * 66 + 8, &wq))) return rc;
+    CU(cudaMemsetAsync(cnt, 0, (3 * 66 + 8) * sizeof(int), stream));
+    CU(cudaMemsetAsync(wq, 0, (6 * 66 + 8) * sizeof(unsigned long long), stream));
     PipeArgs pa{};
     pa.b = sa.b; pa.t = sa.t; pa.o = sa.o; pa.P = sa.P; pa.ctr = sa.ctr;
     pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool[slot].cap;
     pa.ctg = ctg;
     pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data; pa.plan_tree = sa.plan_tree;
     pa.dbg_contig = -1;
-    int *list[3] = {lists, lists + n, lists + 2 * n};
-    int *cnt_act = cnt, *cnt_two = cnt + 66;
+    int *list[4] = {lists, lists + n, lists + 2 * n, lists + 3 * n};
+    int *cnt_act = cnt, *cnt_two = cnt + 66, *cnt_lift = cnt + 2 * 66;
     const int grid = e->sm_count * pipe_ctas_per_sm();
     pa.wq = wq + 1;
     pa.work_base = c0; pa.n_work = c1 - c0;
@@ -416,21 +416,24 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
         pa.list_act = list[lvl & 1]; pa.cnt_act = &cnt_act[lvl];
         pa.list_next = list[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
         pa.list_two = list[2]; pa.cnt_two = &cnt_two[lvl];
-        pa.wq = wq + 2 + 5 * lvl;
+        pa.list_lift = list[3]; pa.cnt_lift = &cnt_lift[lvl];
+        pa.wq = wq + 2 + 6 * lvl;
         launch_pipe_regroup(pa, grid, stream);
-        pa.wq = wq + 3 + 5 * lvl;
+        pa.wq = wq + 3 + 6 * lvl;
         launch_pipe_scores(pa, grid, stream);
-        pa.wq = wq + 4 + 5 * lvl;
+        pa.wq = wq + 4 + 6 * lvl;
         launch_pipe_masks(pa, grid, stream);
-        pa.wq = wq + 5 + 5 * lvl;
+        pa.wq = wq + 5 + 6 * lvl;
         launch_pipe_one(pa, grid, stream);
-        pa.wq = wq + 6 + 5 * lvl;
+        pa.wq = wq + 6 + 6 * lvl;
         launch_pipe_two(pa, grid, stream);
+        pa.wq = wq + 7 + 6 * lvl;
+        launch_pipe_lift(pa, grid, stream);
     }
     pa.list_act = list[L & 1]; pa.cnt_act = &cnt_act[L];
     launch_pipe_leftover(pa, stream);
     CU(cudaGetLastError());
-    e->stats.kernel_launches += 2 + 5 * L;
+    e->stats.kernel_launches += 2 + 6 * L;
     return WFL_OK;
 }
 

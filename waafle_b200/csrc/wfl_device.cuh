@@ -133,8 +133,8 @@ struct PipeArgs {
     unsigned long long *pool_used;
     unsigned long long pool_cap;
     PipeCtg *ctg;                  // [n_contigs]
-    int *list_act, *list_two, *list_next;   // device work lists (contig indices)
-    int *cnt_act, *cnt_two, *cnt_next;
+    int *list_act, *list_two, *list_next, *list_lift;   // device work lists (contig indices)
+    int *cnt_act, *cnt_two, *cnt_next, *cnt_lift;
     int plan_nmax;
     const PlanEntry *plan_index;
     const uint16_t *plan_data;
@@ -152,6 +152,7 @@ void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_lift(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_leftover(const PipeArgs &a, cudaStream_t s);
 int pipe_ctas_per_sm();
 
