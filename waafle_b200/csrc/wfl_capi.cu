@@ -58,6 +58,7 @@ struct wfl_engine {
     bool chunks_streamed = false;        // their H2D copies are in flight on copy_stream (plugin call)
     int resident_split = 1;              // WFL_SPLIT > 1: sub-batches of a resident batch on both compute streams (measured
                                          // slower: kernels of different phases then share the SMs and their instruction caches)
+    bool chunk_fixed = false;            // WFL_CHUNK_MB given: use it as is
     double chunk_shrink = 1.0;           // < 1: geometric tail of the streaming schedule, each chunk >= shrink * its
                                          // predecessor (WFL_CHUNK_SHRINK; measured no better than equal chunks)
     wfl_stats stats{};
@@ -305,7 +306,11 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
     const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
     std::vector<size_t> target;
     if (streaming) {
-        const size_t total = (size_t)hoff[n] * hit_row, full = e->chunk_bytes, first = full / 4;
+        // chunk size: 64 MB, but never more than ~12 chunks per call -- every chunk costs one pass through the
+        // per-level kernel chain (20 launches x levels, each ending on its slowest contig)
+        const size_t total = (size_t)hoff[n] * hit_row;
+        const size_t full = e->chunk_fixed ? e->chunk_bytes : std::max(e->chunk_bytes, total / 12 + 1);
+        const size_t first = std::min(full / 4, e->chunk_bytes);
         std::vector<size_t> tail;
         size_t acc = 0;
         for (size_t t = std::max<size_t>(full / 6, size_t(1) << 20); e->chunk_shrink < 0.999 && t < full && acc + t + first < total;
@@ -330,7 +335,7 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
     while (c0 < n) {
         int64_t c1 = c0;
         size_t est = 0;
-        const size_t goal = k < target.size() ? target[k] : e->chunk_bytes;
+        const size_t goal = k < target.size() ? target[k] : (target.empty() ? e->chunk_bytes : target.back());
         for (;;) {
             // workspace estimate per contig (records + table + level arrays), see wfl_pipeline.cu
             const size_t h = (size_t)(hoff[c1 + 1] - hoff[c1]), g = (size_t)(loff[c1 + 1] - loff[c1]);
@@ -800,7 +805,7 @@ int wfl_create(int device, wfl_engine **out) {
     if (e->mode == 0) { e->threads = 128; e->smem_bytes = 36 * 1024; e->ctas_per_sm = 6; }
     if (const char *k = getenv("WFL_K2")) e->use_tree = std::string(k) == "tree";
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
-    if (const char *k = getenv("WFL_CHUNK_MB")) e->chunk_bytes = (size_t)atoll(k) << 20;
+    if (const char *k = getenv("WFL_CHUNK_MB")) { e->chunk_bytes = (size_t)atoll(k) << 20; e->chunk_fixed = true; }
     if (const char *k = getenv("WFL_SPLIT")) e->resident_split = std::max(1, atoi(k));
     if (const char *k = getenv("WFL_STREAMS")) e->n_slots = atoi(k) >= 2 ? 2 : 1;
     if (const char *k = getenv("WFL_CHUNK_SHRINK")) e->chunk_shrink = std::min(1.0, std::max(0.05, atof(k)));
