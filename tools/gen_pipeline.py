@@ -125,6 +125,14 @@ namespace {
 #ifndef WFL_PIPE_CPSM
 #define WFL_PIPE_CPSM 32   // resident single-warp CTAs per SM the pipeline kernels are compiled for
 #endif
+// The small kernels (regroup, masks, one-clade, lift) wait on dependent workspace loads; they can be compiled
+// with several independent warps per CTA to pass the 32-CTAs-per-SM limit (more warps, fewer registers each).
+#ifndef WFL_LAT_WPC
+#define WFL_LAT_WPC 1      // warps per CTA of the latency-bound kernels
+#endif
+#ifndef WFL_LAT_CPSM
+#define WFL_LAT_CPSM 32    // their resident CTAs per SM
+#endif
 
 // Linear bump arena over one workspace region: region sizes are exact (loci_bytes / record_bytes) or
 // bounds (level_bytes), so carving is a pointer increment plus one capacity compare.
@@ -392,8 +400,8 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
 // The scoring step is cut in three kernels (regroup | K2 | masks) for the same reason the pipeline
 // exists: as one kernel it ran with an SM instruction-cache hit rate of 87 % and the GPC instruction
 // cache at 92 % of its request throughput (profiles/r1_final2_pipeline_kernels_ncu.txt).
-__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_regroup(const PipeArgs a) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_regroup(const PipeArgs a) {
+    const int lane = threadIdx.x & 31;
     const DevParams &P = a.P;
     const DevTax &tax = a.t;
     const int S = P.p.n_systems;
@@ -455,8 +463,8 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeA
 // ---------------------------------------------------------------------------------------------
 // kernel 2c: weak loci (K4), clade rows and gene bitmasks
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_masks(const PipeArgs a) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_masks(const PipeArgs a) {
+    const int lane = threadIdx.x & 31;
     const DevParams &P = a.P;
     const DevTax &tax = a.t;
     const int S = P.p.n_systems;
@@ -499,8 +507,8 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_masks(const PipeAr
 // ---------------------------------------------------------------------------------------------
 // kernel 3: one-clade search
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_one(const PipeArgs a) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_one(const PipeArgs a) {
+    const int lane = threadIdx.x & 31;
     const DevParams &P = a.P;
     const DevTax &tax = a.t;
     const int S = P.p.n_systems;
@@ -590,8 +598,8 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
 // ---------------------------------------------------------------------------------------------
 // kernel 4b: stop (root reached / nothing left) or lift the clade table to the parents (K9, K5)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_lift(const PipeArgs a) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_lift(const PipeArgs a) {
+    const int lane = threadIdx.x & 31;
     const DevParams &P = a.P;
     const DevTax &tax = a.t;
     const int S = P.p.n_systems;
@@ -653,12 +661,12 @@ __global__ void wfl_pipe_leftover(const PipeArgs a) {
 // host side: launch sequence for one sub-batch
 // ---------------------------------------------------------------------------------------------
 void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_prepare<<<grid, 32, 0, s>>>(a); }
-void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_regroup<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_regroup<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
 void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_scores<<<grid, 32, 0, s>>>(a); }
-void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_masks<<<grid, 32, 0, s>>>(a); }
-void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_one<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_masks<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
+void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_one<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_two<<<grid, 32, 0, s>>>(a); }
-void launch_pipe_lift(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_lift<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_lift(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_lift<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
 int pipe_ctas_per_sm() { return WFL_PIPE_CPSM; }
 void launch_pipe_leftover(const PipeArgs &a, cudaStream_t s) { wfl_pipe_leftover<<<64, 256, 0, s>>>(a); }
 
