@@ -249,6 +249,33 @@ def test_alternate_kernels_stay_bit_exact(mode, monkeypatch):
     assert not helpers.compare_results(ref, outs[mode][0])
 
 
+def test_many_small_chunks_on_two_streams(monkeypatch):
+    """Plugin call cut into ~50 chunks of 1 MB that alternate between the two compute streams (and, with a
+    64 MB workspace pool, into even smaller sub-batches): same bytes as the C restatement and as one chunk."""
+    from waafle_b200 import synth
+    from waafle_b200.engine import Engine
+    data = synth.generate_config("cfg3", n_contigs=3000, seed=71)
+    tax = data.taxonomy()
+    batch = data.to_batch(tax)
+    P = helpers.params_for(dict(weak_loci="penalize", range=0.2), 0)
+    ref = c_oracle.score_batch(P, tax, batch)
+    for env in (dict(WFL_CHUNK_MB="1"), dict(WFL_CHUNK_MB="1", WFL_STREAMS="1"), dict(WFL_CHUNK_MB="2", WFL_POOL_MB="64"),
+                dict(WFL_CHUNK_MB="4096")):
+        for k in ("WFL_CHUNK_MB", "WFL_STREAMS", "WFL_POOL_MB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = Engine(0, P, tax)
+        got = eng.score_batch(batch)
+        again = eng.score_batch(batch)
+        st = eng.stats()
+        eng.close()
+        assert not helpers.compare_results(ref, got), env
+        assert not helpers.compare_results(ref, again), env
+        if env.get("WFL_CHUNK_MB") == "1":
+            assert st["kernel_launches"] > 20 * 20   # many chunks really ran
+
+
 def test_small_workspace_pool_replays(monkeypatch):
     """A pool too small for a long contig: it is replayed by the monolithic kernel
     (workspace_retries > 0) and the results do not change (members included)."""
