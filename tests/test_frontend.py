@@ -91,3 +91,53 @@ def test_bad_rows_die(tmp_path):
     g.write_text("c1\tx\tgene\t1\n")
     with pytest.raises(SystemExit):
         parsers.read_gff_loci(str(g))
+
+
+def test_arrow_and_pandas_front_ends_agree(tmp_path, monkeypatch):
+    """The Arrow reader / string kernels (fast path) and the pandas + per-header Python path (fallback) give
+    the same hit table and the same packed batch, for plain and gzip-compressed blastout files."""
+    import gzip
+    import shutil
+    from waafle_b200 import utils
+    if parsers.pa is None:
+        pytest.skip("pyarrow not importable")
+    data = helpers.synth_case(dict(config="cfg5", n_contigs=60, seed=9, over={}))
+    files = data.write_files(str(tmp_path), "a")
+    gz = dict(files, blastout=files["blastout"] + ".gz")
+    with open(files["blastout"], "rb") as a, gzip.open(gz["blastout"], "wb") as b:
+        shutil.copyfileobj(a, b)
+
+    def load(f):
+        hits = parsers.read_blast_hits(f["blastout"])
+        loci = parsers.read_gff_loci(f["gff"])
+        tax = taxonomy.Taxonomy(f["taxonomy"]).build(set(hits.taxon))
+        return hits, packing.pack(utils.read_contig_lengths(f["contigs"]), loci, hits, tax)
+
+    fast, fast_gz = load(files), load(gz)
+    assert fast[0].taxon_codes is not None and fast[0].qseqid_codes is not None
+    for name in ("pa", "pc", "pacsv"):
+        monkeypatch.setattr(parsers, name, None)
+    slow = load(files)
+    assert slow[0].taxon_codes is None
+    for hits, batch in (fast, fast_gz):
+        for k in ("qstart", "qend", "score", "scov_modified", "strand", "sysmask"):
+            assert np.array_equal(getattr(hits, k), getattr(slow[0], k)), k
+        assert list(hits.taxon) == list(slow[0].taxon) and list(hits.qseqid) == list(slow[0].qseqid)
+        assert hits.systems == slow[0].systems
+        for i in range(0, len(hits), 37):
+            assert hits.sseqid_annotations[int(hits.sseqid_id[i])] == slow[0].sseqid_annotations[int(slow[0].sseqid_id[i])]
+            assert hits.sseqid_names[int(hits.sseqid_id[i])] == slow[0].sseqid_names[int(slow[0].sseqid_id[i])]
+        for k, v in batch.arrays().items():
+            assert np.array_equal(v, slow[1].arrays()[k]), k
+
+
+def test_bad_subject_header_dies_on_both_paths(tmp_path, monkeypatch):
+    row = "c1\tGENE_WITHOUT_TAXON\t5000\t1000\t900\t1\t900\t1\t900\t95.0\t855\t0\t0.0\t1500\tplus\n"
+    p = tmp_path / "h.blastout"
+    p.write_text(row)
+    with pytest.raises(SystemExit):
+        parsers.read_blast_hits(str(p))
+    for name in ("pa", "pc", "pacsv"):
+        monkeypatch.setattr(parsers, name, None)
+    with pytest.raises(SystemExit):
+        parsers.read_blast_hits(str(p))

@@ -76,9 +76,14 @@ class Batch:
                 + 40 * self.n_contigs + self.n_loci * (1 + 4 * n_systems))
 
 
-def _group(names, index, what):
-    """Map row -> contig index; unknown contigs are warned about and dropped like OS:921-923."""
-    cid = np.fromiter((index.get(n, -1) for n in names), dtype=np.int64, count=len(names))
+def _group(names, index, what, codes=None, code_names=None):
+    """Map row -> contig index; unknown contigs are warned about and dropped like OS:921-923.
+    `codes` / `code_names`: optional dictionary encoding of `names` (one lookup per distinct name)."""
+    if codes is not None and len(codes) == len(names):
+        lut = np.fromiter((index.get(n, -1) for n in code_names), dtype=np.int64, count=len(code_names))
+        cid = lut[codes] if len(codes) else np.zeros(0, dtype=np.int64)
+    else:
+        cid = np.fromiter((index.get(n, -1) for n in names), dtype=np.int64, count=len(names))
     if len(cid):
         starts = np.r_[True, names[1:] != names[:-1]]
         for n in names[starts & (cid < 0)]:
@@ -98,7 +103,7 @@ def pack(contig_lengths, loci, hits, taxonomy):
     locus_off = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(lc[lrow], minlength=n), out=locus_off[1:])
 
-    hc = _group(hits.qseqid, index, "blastout")
+    hc = _group(hits.qseqid, index, "blastout", getattr(hits, "qseqid_codes", None), getattr(hits, "qseqid_names", None))
     if len(hc):
         # the reference assumes the blastout is grouped by query (UT:255-258)
         starts = np.r_[True, hits.qseqid[1:] != hits.qseqid[:-1]]
@@ -111,8 +116,12 @@ def pack(contig_lengths, loci, hits, taxonomy):
     hit_off = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(hc[hrow], minlength=n), out=hit_off[1:])
 
-    taxon = np.fromiter((taxonomy.index[t] for t in hits.taxon[hrow]), dtype=np.int32,
-                        count=len(hrow))
+    if getattr(hits, "taxon_codes", None) is not None:
+        tlut = np.fromiter((taxonomy.index[t] for t in hits.taxon_names), dtype=np.int32, count=len(hits.taxon_names))
+        taxon = tlut[hits.taxon_codes[hrow]] if len(hrow) else np.zeros(0, dtype=np.int32)
+    else:
+        taxon = np.fromiter((taxonomy.index[t] for t in hits.taxon[hrow]), dtype=np.int32,
+                            count=len(hrow))
     return Batch(
         hit_off=hit_off, locus_off=locus_off,
         hit_qstart=np.ascontiguousarray(hits.qstart[hrow]),
