@@ -419,6 +419,51 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_regro
 #pragma unroll 1
         for (int once = 0; once < 1; ++once) {
 @F@
+            if (a.k2_desc != nullptr) {
+                // ---- K2 work items: one descriptor per group with records, appended to the sub-batch's list
+                const int nreal = spike ? Ngrp - G : Ngrp;   // the G spiked Unknown rows carry no records
+                // reserve nreal slots with ONE atomic add (a compare-and-swap loop on this counter serialises the
+                // whole grid).  A contig that does not fit fills its in-range slots with null items, which the K2
+                // kernel skips, and is replayed by the warp kernel.
+                unsigned long long dbase = 0;
+                if (lane == 0) dbase = atomicAdd(&a.k2_meta->count, (unsigned long long)nreal);
+                dbase = __shfl_sync(FULL, dbase, 0);
+                if (dbase + (unsigned long long)nreal > a.k2_cap) {
+                    K2Desc d{};
+                    unsigned int nfill = 0;
+#pragma unroll 1
+                    for (unsigned long long i = dbase + lane; i < a.k2_cap; i += 32) {
+                        a.k2_desc[i] = d;
+                        a.k2_keys[i] = 0u;
+                        ++nfill;
+                    }
+                    (void)nfill;
+                    overflow = true;
+                    break;
+                }
+                int wbase = 0;
+#pragma unroll 1
+                for (int gb = 0; gb < Ngrp; gb += 32) {
+                    const int g = gb + lane;
+                    const bool f = g < Ngrp && g_rs[g] >= 0;
+                    const u32 m = __ballot_sync(FULL, f);
+                    if (f) {
+                        const int loc = g_loc[g], rs = g_rs[g], re = g_re[g], nleaf = l_nleaf[loc];
+                        const int kc = re - rs <= 1 ? 0 : (re - rs <= 3 ? 1 : (re - rs <= 8 ? 2 : 3));
+                        const int key = (min(nleaf, 127) << 2) | kc;
+                        K2Desc d;
+                        d.sa = s_a; d.plan = l_plan[loc]; d.out = &g_score[g];
+                        d.maxb = cl_id[g_t[g]] != tax.unknown ? &maxb[loc] : nullptr;
+                        d.d_sb = (int)(s_b - s_a);
+                        d.d_sv = (int)(reinterpret_cast<const char *>(s_v) - reinterpret_cast<const char *>(s_a));
+                        d.rs = rs; d.re = re; d.n = l_len[loc]; d.nleaf = nleaf; d.k8 = l_k8[loc]; d.key = (unsigned)key;
+                        const unsigned long long slot = dbase + wbase + __popc(m & lt_mask());
+                        a.k2_desc[slot] = d;
+                        a.k2_keys[slot] = (unsigned)key;
+                    }
+                    wbase += __popc(m);
+                }
+            }
         }
         if (lane == 0) {
             atomicAdd(&a.ctr->groups, (unsigned long long)n_groups);
@@ -455,6 +500,96 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeA
         DECL_GROUPS
         (void)cur; (void)gs; (void)T; (void)lifts; (void)l_raw; (void)l0; (void)ign; (void)um; (void)r_t; (void)r_loc;
 @G2@
+        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(clock64() - t_start));
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels 2b': K2 over the sub-batch's GLOBAL group list.  Counting sort of the descriptors by
+// (leaf count, record-count class), then lane per group: the lanes of a warp walk the same leaf plan
+// whatever contig their group belongs to (per contig, lanes met different plans and a partly filled last
+// round: 11 of 32 threads active per instruction).
+// ---------------------------------------------------------------------------------------------
+constexpr int K2_TILE = 4096;   // items per block pass of the counting sort (256 threads x 16)
+
+// histogram of the sort keys: per-block counts in shared memory, one flush per block
+__global__ void __launch_bounds__(256) wfl_pipe_k2hist(const PipeArgs a) {
+    __shared__ unsigned int cnt[K2_KEYS];
+    const unsigned long long n = a.k2_meta->count < a.k2_cap ? a.k2_meta->count : a.k2_cap;
+    for (int k = threadIdx.x; k < K2_KEYS; k += 256) cnt[k] = 0;
+    __syncthreads();
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
+        atomicAdd(&cnt[a.k2_keys[i] & (K2_KEYS - 1)], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < K2_KEYS; k += 256)
+        if (cnt[k]) atomicAdd(&a.k2_meta->hist[k], cnt[k]);
+}
+
+__global__ void wfl_pipe_k2scan(const PipeArgs a) {
+    __shared__ unsigned int part[K2_KEYS];
+    const int t = threadIdx.x;   // K2_KEYS threads
+    const unsigned int h = a.k2_meta->hist[t];
+    part[t] = h;
+    __syncthreads();
+    for (int o = 1; o < K2_KEYS; o <<= 1) {
+        unsigned int v = t >= o ? part[t - o] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    a.k2_meta->cursor[t] = part[t] - h;
+}
+
+// scatter: a block ranks a tile of items per key in shared memory, reserves one range per key with a single
+// global atomic, and writes the item indices to their sorted positions
+__global__ void __launch_bounds__(256) wfl_pipe_k2scatter(const PipeArgs a) {
+    __shared__ unsigned int cnt[K2_KEYS], base[K2_KEYS];
+    const unsigned long long n = a.k2_meta->count < a.k2_cap ? a.k2_meta->count : a.k2_cap;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * K2_TILE; t0 < n; t0 += (unsigned long long)gridDim.x * K2_TILE) {
+        for (int k = threadIdx.x; k < K2_KEYS; k += 256) cnt[k] = 0;
+        __syncthreads();
+        unsigned int key[K2_TILE / 256], rk[K2_TILE / 256];
+#pragma unroll
+        for (int q = 0; q < K2_TILE / 256; ++q) {
+            const unsigned long long i = t0 + (unsigned long long)q * 256 + threadIdx.x;
+            key[q] = i < n ? (a.k2_keys[i] & (K2_KEYS - 1)) : 0xffffffffu;
+            rk[q] = i < n ? atomicAdd(&cnt[key[q]], 1u) : 0u;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < K2_KEYS; k += 256)
+            if (cnt[k]) base[k] = atomicAdd(&a.k2_meta->cursor[k], cnt[k]);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < K2_TILE / 256; ++q) {
+            const unsigned long long i = t0 + (unsigned long long)q * 256 + threadIdx.x;
+            if (i < n) a.k2_order[base[key[q]] + rk[q]] = (unsigned int)i;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_k2(const PipeArgs a) {
+    const int lane = threadIdx.x;
+    const unsigned long long n = a.k2_meta->count < a.k2_cap ? a.k2_meta->count : a.k2_cap;
+#pragma unroll 1
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.k2_meta->take, 32ull);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const long long t_start = clock64();
+        const unsigned long long i = base + lane;
+        if (i < n) {
+            const K2Desc d = a.k2_desc[a.k2_order[i]];
+            if (d.out != nullptr) {
+            const double sc = group_mean(d.sa, d.sa + d.d_sb,
+                                         reinterpret_cast<const double *>(reinterpret_cast<const char *>(d.sa) + d.d_sv),
+                                         d.rs, d.re, d.n, true, d.k8, d.plan, d.nleaf);
+            *d.out = sc;
+            if (d.maxb != nullptr) atomicMax(d.maxb, dbits(sc));   // waafle_orgscorer.py:409-411
+            }
+        }
         if (lane == 0) atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(clock64() - t_start));
         __syncwarp();
     }
@@ -663,6 +798,12 @@ __global__ void wfl_pipe_leftover(const PipeArgs a) {
 void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_prepare<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_regroup<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
 void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_scores<<<grid, 32, 0, s>>>(a); }
+void launch_pipe_k2sort(const PipeArgs &a, int grid, cudaStream_t s) {
+    wfl_pipe_k2hist<<<grid / 8 + 1, 256, 0, s>>>(a);
+    wfl_pipe_k2scan<<<1, K2_KEYS, 0, s>>>(a);
+    wfl_pipe_k2scatter<<<grid / 8 + 1, 256, 0, s>>>(a);
+}
+void launch_pipe_k2(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_k2<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_masks<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
 void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_one<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_two<<<grid, 32, 0, s>>>(a); }

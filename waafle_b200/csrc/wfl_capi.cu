@@ -52,7 +52,8 @@ struct wfl_engine {
     bool use_tree = false;              // WFL_K2=tree: K2 by tree walk with constant-subtree skipping (parity-tested,
                                         // but slower than the flat leaf plan on B200: more local-memory state)
     size_t pipe_pool_bytes = size_t(8192) << 20;
-    Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2];
+    Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2], k2_desc[2], k2_order[2], k2_keys[2], k2_meta[2];
+    bool k2_global = true;              // WFL_K2=contig: K2 per contig (wfl_pipe_scores) instead of the sorted global group list
     std::vector<int64_t> h_hit_off, h_locus_off;
     std::vector<int64_t> chunks;         // contig boundaries of the sub-batches of the current batch
     bool chunks_streamed = false;        // their H2D copies are in flight on copy_stream (plugin call)
@@ -409,6 +410,17 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool[slot].cap;
     pa.ctg = ctg;
     pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data; pa.plan_tree = sa.plan_tree;
+    K2Meta *k2meta = nullptr;
+    pa.k2_desc = nullptr;
+    if (e->k2_global && !e->use_tree) {
+        const size_t cap = (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]) * 5 / 4 + 4096;
+        if ((rc = outbuf(e, e->k2_desc[slot], cap, &pa.k2_desc))) return rc;
+        if ((rc = outbuf(e, e->k2_order[slot], cap, &pa.k2_order))) return rc;
+        if ((rc = outbuf(e, e->k2_keys[slot], cap, &pa.k2_keys))) return rc;
+        if ((rc = outbuf(e, e->k2_meta[slot], 66, &k2meta))) return rc;
+        pa.k2_cap = cap;
+        CU(cudaMemsetAsync(k2meta, 0, 66 * sizeof(K2Meta), stream));
+    }
     pa.dbg_contig = -1;
     int *list[4] = {lists, lists + n, lists + 2 * n, lists + 3 * n};
     int *cnt_act = cnt, *cnt_two = cnt + 66, *cnt_lift = cnt + 2 * 66;
@@ -422,10 +434,16 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
         pa.list_next = list[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
         pa.list_two = list[2]; pa.cnt_two = &cnt_two[lvl];
         pa.list_lift = list[3]; pa.cnt_lift = &cnt_lift[lvl];
+        pa.k2_meta = k2meta ? k2meta + lvl : nullptr;
         pa.wq = wq + 2 + 6 * lvl;
         launch_pipe_regroup(pa, grid, stream);
         pa.wq = wq + 3 + 6 * lvl;
-        launch_pipe_scores(pa, grid, stream);
+        if (pa.k2_desc != nullptr) {
+            launch_pipe_k2sort(pa, grid, stream);
+            launch_pipe_k2(pa, grid, stream);
+        } else {
+            launch_pipe_scores(pa, grid, stream);
+        }
         pa.wq = wq + 4 + 6 * lvl;
         launch_pipe_masks(pa, grid, stream);
         pa.wq = wq + 5 + 6 * lvl;
@@ -438,7 +456,7 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     pa.list_act = list[L & 1]; pa.cnt_act = &cnt_act[L];
     launch_pipe_leftover(pa, stream);
     CU(cudaGetLastError());
-    e->stats.kernel_launches += 2 + 6 * L;
+    e->stats.kernel_launches += 2 + (pa.k2_desc != nullptr ? 9 : 6) * L;
     return WFL_OK;
 }
 
@@ -803,7 +821,7 @@ int wfl_create(int device, wfl_engine **out) {
         e->mode = m == "v1" ? 0 : m == "v2" ? 1 : 2;
     }
     if (e->mode == 0) { e->threads = 128; e->smem_bytes = 36 * 1024; e->ctas_per_sm = 6; }
-    if (const char *k = getenv("WFL_K2")) e->use_tree = std::string(k) == "tree";
+    if (const char *k = getenv("WFL_K2")) { e->use_tree = std::string(k) == "tree"; e->k2_global = std::string(k) != "contig"; }
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
     if (const char *k = getenv("WFL_CHUNK_MB")) { e->chunk_bytes = (size_t)atoll(k) << 20; e->chunk_fixed = true; }
     if (const char *k = getenv("WFL_SPLIT")) e->resident_split = std::max(1, atoi(k));
@@ -831,6 +849,7 @@ void wfl_destroy(wfl_engine *e) {
     fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data); fr(e->plan_tree);
     for (int q = 0; q < 2; ++q) { fr(e->pipe_pool[q]); fr(e->pipe_lists[q]); fr(e->pipe_cnt[q]); fr(e->pipe_wq[q]); }
     fr(e->pipe_ctg);
+    for (int q = 0; q < 2; ++q) { fr(e->k2_desc[q]); fr(e->k2_order[q]); fr(e->k2_keys[q]); fr(e->k2_meta[q]); }
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->chunk_ev) cudaEventDestroy(ev);
     if (e->ev_join) cudaEventDestroy(e->ev_join);

@@ -121,6 +121,26 @@ struct PipeCtg {
     int state;
 };
 
+// One (clade, locus) group of one contig as a self-contained K2 work item (64 bytes): the regroup kernel emits
+// them into a per-sub-batch list, a counting sort by (leaf count, record-count class) orders them, and the K2
+// kernel walks the list lane per group, so that the 32 lanes of a warp follow the same leaf plan.
+struct K2Desc {
+    const int *sa;                 // slice starts of the contig's records in group order; ends at sa + d_sb
+    const uint16_t *plan;          // leaf plan of the gene length
+    double *out;                   // g_score slot
+    unsigned long long *maxb;      // per-locus max (order-preserving bits); null for the Unknown clade
+    int d_sb, d_sv;                // sb = sa + d_sb (ints); sv = (double *)((char *)sa + d_sv)
+    int rs, re, n, nleaf;
+    unsigned int k8;
+    unsigned int key;
+};
+constexpr int K2_KEYS = 512;       // (min(nleaf, 127) << 2) | record-count class
+struct K2Meta {                    // one per taxonomy level, zeroed per sub-batch
+    unsigned int hist[K2_KEYS];
+    unsigned int cursor[K2_KEYS];
+    unsigned long long count, take;
+};
+
 struct PipeArgs {
     DevBatch b;
     DevTax t;
@@ -139,6 +159,11 @@ struct PipeArgs {
     const PlanEntry *plan_index;
     const uint16_t *plan_data;
     const TreeEntry *plan_tree;
+    K2Desc *k2_desc;               // null: K2 per contig (wfl_pipe_scores)
+    unsigned int *k2_order;
+    unsigned int *k2_keys;         // sort key of every descriptor (compact copy for the counting sort)
+    unsigned long long k2_cap;
+    K2Meta *k2_meta;               // this level's
     long long dbg_contig;
     int32_t *dbg_clade, *dbg_locus;
     double *dbg_score;
@@ -150,6 +175,8 @@ void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s);
+void launch_pipe_k2sort(const PipeArgs &a, int grid, cudaStream_t s);   // scan + scatter
+void launch_pipe_k2(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_one(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_two(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_lift(const PipeArgs &a, int grid, cudaStream_t s);
