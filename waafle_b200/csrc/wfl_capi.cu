@@ -31,7 +31,7 @@ struct wfl_engine {
     int n_slots = 2;                     // plugin call: sub-batches alternate between two compute streams
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> chunk_ev;
-    size_t chunk_bytes = size_t(64) << 20;   // H2D chunk size of the pipelined plugin call (measured best: profiles/README.md)
+    size_t chunk_bytes = size_t(96) << 20;   // H2D chunk size of the pipelined plugin call (measured best: profiles/README.md)
     std::string err;
     bool have_params = false, have_tax = false, have_batch = false, have_results = false;
     DevParams P{};
@@ -307,7 +307,7 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
     const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
     std::vector<size_t> target;
     if (streaming) {
-        // chunk size: 64 MB, but never more than ~12 chunks per call -- every chunk costs one pass through the
+        // chunk size: 96 MB, but never more than ~12 chunks per call -- every chunk costs one pass through the
         // per-level kernel chain (20 launches x levels, each ending on its slowest contig)
         const size_t total = (size_t)hoff[n] * hit_row;
         const size_t full = e->chunk_fixed ? e->chunk_bytes : std::max(e->chunk_bytes, total / 12 + 1);
