@@ -211,12 +211,14 @@ def test_tree_walk_gene_scores_bit_exact(monkeypatch):
     batch = data.to_batch(tax)
     P = helpers.params_for({}, 0)
     outs = []
-    for k2 in ("leaf", "tree"):
+    # "global": K2 over the sorted global group list (default); "contig": K2 per contig; "tree": per contig, tree walk
+    for k2 in ("global", "contig", "tree"):
         monkeypatch.setenv("WFL_K2", k2)
         eng = Engine(0, P, tax)
         outs.append(eng.score_batch(batch))
         eng.close()
     assert not helpers.compare_results(outs[0], outs[1])
+    assert not helpers.compare_results(outs[0], outs[2])
     batch2, tax2 = helpers.adversarial_batches()["knife_edge"]
     eng = Engine(0, helpers.params_for({}, 1), tax2)
     got = eng.score_batch(batch2)
