@@ -322,7 +322,7 @@ def main():
                     "last_call_ms": {"h2d_window": st_e2e["ms_h2d"], "kernels_window": st_e2e["ms_kernels"],
                                      "d2h": st_e2e["ms_d2h"]}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "wfl_pipe_* (all launches of one step: prepare, then regroup/scores/masks/one/two/lift per taxonomy level; the K2 kernel wfl_pipe_scores is ~40% of it)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "wfl_pipe_* (all launches of one step: prepare, then regroup / K2 sort / k2 / masks / one / two / lift per taxonomy level; the K2 kernel wfl_pipe_k2 is ~30% of it)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms": score_ms / args.steps},
