@@ -40,53 +40,89 @@ def _tails_field(taxonomy, members, lca):
     return "; ".join(sorted(items))
 
 
+def _winner_annotations(batch, hits, res, systems):
+    """{(locus row j, system index s): value} for every transferred annotation.  The subject headers of all
+    winning hits are fetched and parsed once (they live in an Arrow array on the fast front end)."""
+    aw = np.asarray(res["ann_winner"])
+    if aw.ndim != 2 or aw.shape[1] == 0 or hits is None or not systems:
+        return {}
+    jj, ss = np.nonzero(aw >= 0)
+    if len(jj) == 0:
+        return {}
+    sid = np.asarray(hits.sseqid_id)[np.asarray(batch.hit_row)[aw[jj, ss]]]
+    uniq = np.unique(sid)
+    parsed = {int(u): hits.sseqid_annotations[int(u)] for u in uniq}
+    return {(int(j), int(s)): parsed[int(i)][systems[int(s)]] for j, s, i in zip(jj.tolist(), ss.tolist(), sid.tolist())}
+
+
 def build_records(batch, loci, hits, taxonomy, res):
     """One dict per contig (FASTA order) with the reference's row values, unformatted."""
     names = taxonomy.names
     S = res["ann_winner"].shape[1] if res["ann_winner"].ndim == 2 else 0
     systems = list(hits.systems)[:S] if hits is not None else []
+    # plain Python lists: the loop below touches every element once, and numpy scalar access is ~10x slower
+    locus_off = np.asarray(batch.locus_off).tolist()
+    flags = np.asarray(res["locus_flags"]).tolist()
+    locus_row = np.asarray(batch.locus_row).tolist()
+    calls = np.asarray(res["call"]).tolist()
+    lifts = np.asarray(res["lifts"]).tolist()
+    lengths = np.asarray(batch.contig_lengths).tolist()
+    member_off = np.asarray(res["member_off"]).tolist()
+    n_members_a = np.asarray(res["n_members_a"]).tolist()
+    members = np.asarray(res["members"]).tolist()
+    clade1, clade2, lca = (np.asarray(res[k]).tolist() for k in ("clade1", "clade2", "lca"))
+    crit, rank = np.asarray(res["crit"]).tolist(), np.asarray(res["rank"]).tolist()
+    direction = np.asarray(res["direction"]).tolist()
+    synteny = bytes(np.asarray(res["synteny"], dtype=np.uint8)).decode("latin-1")
+    winners = _winner_annotations(batch, hits, res, systems)
+    lineage_cache = {}
+
+    def lineage(c):
+        if c not in lineage_cache:
+            lineage_cache[c] = "|".join(taxonomy.get_lineage(c))
+        return lineage_cache[c]
+
     records = []
     for c in range(batch.n_contigs):
-        l0, l1 = int(batch.locus_off[c]), int(batch.locus_off[c + 1])
-        kept = [j for j in range(l0, l1) if res["locus_flags"][j] & FLAG_RETAINED]
+        l0, l1 = locus_off[c], locus_off[c + 1]
+        kept = [j for j in range(l0, l1) if flags[j] & FLAG_RETAINED]
         rec = dict(
-            contig_name=batch.contig_names[c], call=CALLS[int(res["call"][c])],
-            contig_length=int(batch.contig_lengths[c]),
-            loci="|".join(loci.code(int(batch.locus_row[j])) for j in kept),
-            ignore=[bool(res["locus_flags"][j] & FLAG_IGNORED) for j in kept],
-            lifts=int(res["lifts"][c]))
+            contig_name=batch.contig_names[c], call=CALLS[calls[c]],
+            contig_length=lengths[c],
+            loci="|".join(loci.code(locus_row[j]) for j in kept),
+            ignore=[bool(flags[j] & FLAG_IGNORED) for j in kept],
+            lifts=lifts[c])
         ann = []
         for j in kept:
             d = {}
             for s in range(S):
-                w = int(res["ann_winner"][j, s])
-                if w >= 0:
-                    sid = int(hits.sseqid_id[int(batch.hit_row[w])])
-                    d[systems[s]] = hits.sseqid_annotations[sid][systems[s]]
+                v = winners.get((j, s))
+                if v is not None:
+                    d[systems[s]] = v
             ann.append(d)
         rec["annotations"] = ann
-        call = int(res["call"][c])
+        call = calls[c]
         if call:
-            m0, m1 = int(res["member_off"][c]), int(res["member_off"][c + 1])
-            na = int(res["n_members_a"][c])
-            mem = res["members"][m0:m1]
-            c1 = int(res["clade1"][c])
-            syn = bytes(res["synteny"][kept]).decode("ascii") if kept else ""
+            m0, m1 = member_off[c], member_off[c + 1]
+            na = n_members_a[c]
+            mem = members[m0:m1]
+            c1 = clade1[c]
+            syn = "".join(synteny[j] for j in kept)
             if call == 1:
-                rec.update(min_score=float(res["crit"][c]), avg_score=float(res["rank"][c]),
+                rec.update(min_score=crit[c], avg_score=rank[c],
                            synteny=syn, clade=names[c1],
                            melded=_tails_field(taxonomy, mem[:na], c1),
-                           taxonomy="|".join(taxonomy.get_lineage(c1)))
+                           taxonomy=lineage(c1))
             else:
-                c2 = int(res["clade2"][c])
-                rec.update(min_max_score=float(res["crit"][c]),
-                           avg_max_score=float(res["rank"][c]), synteny=syn,
-                           direction=DIRECTIONS[int(res["direction"][c])],
-                           clade_A=names[c1], clade_B=names[c2], lca=names[int(res["lca"][c])],
+                c2 = clade2[c]
+                rec.update(min_max_score=crit[c],
+                           avg_max_score=rank[c], synteny=syn,
+                           direction=DIRECTIONS[direction[c]],
+                           clade_A=names[c1], clade_B=names[c2], lca=names[lca[c]],
                            melded_A=_tails_field(taxonomy, mem[:na], c1),
                            melded_B=_tails_field(taxonomy, mem[na:], c2),
-                           taxonomy_A="|".join(taxonomy.get_lineage(c1)),
-                           taxonomy_B="|".join(taxonomy.get_lineage(c2)))
+                           taxonomy_A=lineage(c1),
+                           taxonomy_B=lineage(c2))
         records.append(rec)
     return records
 
