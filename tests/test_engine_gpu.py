@@ -278,6 +278,26 @@ def test_many_small_chunks_on_two_streams(monkeypatch):
             assert st["kernel_launches"] > 20 * 20   # many chunks really ran
 
 
+def test_group_list_overflow_replays(monkeypatch):
+    """A K2 group list that is far too small (WFL_K2_CAP): contigs that do not fit are replayed by the warp
+    kernel, the list never holds unwritten items, and the results do not change."""
+    from waafle_b200 import synth
+    from waafle_b200.engine import Engine
+    data = synth.generate_config("cfg2", n_contigs=600, seed=77)
+    tax = data.taxonomy()
+    batch = data.to_batch(tax)
+    P = helpers.params_for(dict(weak_loci="assign-unknown"), 0)
+    ref = c_oracle.score_batch(P, tax, batch)
+    for cap in ("3000", "1"):
+        monkeypatch.setenv("WFL_K2_CAP", cap)
+        eng = Engine(0, P, tax)
+        got = eng.score_batch(batch)
+        st = eng.stats()
+        eng.close()
+        assert st["workspace_retries"] > 0
+        assert not helpers.compare_results(ref, got), cap
+
+
 def test_small_workspace_pool_replays(monkeypatch):
     """A pool too small for a long contig: it is replayed by the monolithic kernel
     (workspace_retries > 0) and the results do not change (members included)."""

@@ -53,6 +53,7 @@ struct wfl_engine {
                                         // but slower than the flat leaf plan on B200: more local-memory state)
     size_t pipe_pool_bytes = size_t(8192) << 20;
     Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2], k2_desc[2], k2_order[2], k2_keys[2], k2_meta[2];
+    size_t k2_cap_override = 0;         // WFL_K2_CAP: descriptor capacity per sub-batch (test hook for the overflow path)
     bool k2_global = true;              // WFL_K2=contig: K2 per contig (wfl_pipe_scores) instead of the sorted global group list
     std::vector<int64_t> h_hit_off, h_locus_off;
     std::vector<int64_t> chunks;         // contig boundaries of the sub-batches of the current batch
@@ -413,7 +414,8 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     K2Meta *k2meta = nullptr;
     pa.k2_desc = nullptr;
     if (e->k2_global && !e->use_tree) {
-        const size_t cap = (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]) * 5 / 4 + 4096;
+        const size_t cap = e->k2_cap_override ? e->k2_cap_override
+                                             : (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]) * 5 / 4 + 4096;
         if ((rc = outbuf(e, e->k2_desc[slot], cap, &pa.k2_desc))) return rc;
         if ((rc = outbuf(e, e->k2_order[slot], cap, &pa.k2_order))) return rc;
         if ((rc = outbuf(e, e->k2_keys[slot], cap, &pa.k2_keys))) return rc;
@@ -822,6 +824,7 @@ int wfl_create(int device, wfl_engine **out) {
     }
     if (e->mode == 0) { e->threads = 128; e->smem_bytes = 36 * 1024; e->ctas_per_sm = 6; }
     if (const char *k = getenv("WFL_K2")) { e->use_tree = std::string(k) == "tree"; e->k2_global = std::string(k) != "contig"; }
+    if (const char *k = getenv("WFL_K2_CAP")) e->k2_cap_override = (size_t)std::max<long long>(0, atoll(k));
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
     if (const char *k = getenv("WFL_CHUNK_MB")) { e->chunk_bytes = (size_t)atoll(k) << 20; e->chunk_fixed = true; }
     if (const char *k = getenv("WFL_SPLIT")) e->resident_split = std::max(1, atoi(k));
