@@ -42,9 +42,9 @@ def parse_args():
     ap.add_argument("--contigs", type=int, default=None, help="contigs per GPU (default: config size)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="contigs in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--threads", type=int, default=0)
-    ap.add_argument("--smem", type=int, default=0)
-    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--exact", action="store_true", help="exact pipeline for every contig (bit-exact crit / rank)")
+    ap.add_argument("--wide", action="store_true", help="e2e leg with the wide 29 B/hit wire format")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (wfl_set_option)")
     return ap.parse_args()
 
 
@@ -215,7 +215,11 @@ def main():
 
     from waafle_b200.engine import Engine
     eng = Engine(local_rank, params, tax)
-    eng.configure(args.threads, args.smem, args.ctas_per_sm)
+    if args.exact:
+        eng.set_option("exact", 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,14 +250,19 @@ def main():
     if c_ref is not None:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from helpers import compare_results
-        diffs = compare_results(c_ref, res)
+        rtol = 0.0 if args.exact else 1e-12
+        diffs = compare_results(c_ref, res, score_rtol=rtol)
         parity = {"checked_contigs": batch.n_contigs, "against": "oracle/orgscorer_oracle.c",
-                  "bit_exact": not diffs, "diffs": [str(d)[:160] for d in diffs[:3]]}
+                  "bit_exact": not diffs, "score_rtol": rtol,
+                  "what": "calls, clades, synteny, loci flags, members, annotation winners bit-exact; crit / rank within score_rtol",
+                  "diffs": [str(d)[:160] for d in diffs[:3]]}
 
     # ---- end-to-end leg: pinned host buffers through the plugin call ----
     from waafle_b200.engine import PinnedArena
     pin = PinnedArena()
-    harr = {k: pin.like(np.ascontiguousarray(v)) for k, v in batch.arrays().items()}
+    packed = (not args.wide) and batch.can_pack(len(tax.tables()["parent"]), params.n_systems)
+    wire = batch.to_packed(params.min_scov) if packed else batch.arrays()
+    harr = {k: pin.like(np.ascontiguousarray(v)) for k, v in wire.items()}
     eng.use_pinned_results(True)
     h2d_bytes = int(sum(v.nbytes for v in harr.values()))
     out = eng.score_batch(harr)
@@ -318,7 +327,7 @@ def main():
                        "wall_ms_per_step": wall_ms / args.steps},
             "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step": e2e_ms / args.steps, "wire_format": "packed 14 B/hit" if packed else "wide 29 B/hit",
                     "last_call_ms": {"h2d_window": st_e2e["ms_h2d"], "kernels_window": st_e2e["ms_kernels"],
                                      "d2h": st_e2e["ms_d2h"]}},
             "gpu_launches": int(launches),
@@ -332,7 +341,8 @@ def main():
             "calls": {"lgt": int(res["call_counts"][0]), "no_lgt": int(res["call_counts"][1]),
                       "unclassified": int(res["call_counts"][2])},
             "engine_stats": {k: st[k] for k in ("matched_pairs", "groups", "levels", "pairs_tested",
-                                                "pairs_scored", "workspace_retries", "smem_contigs")},
+                                                "pairs_scored", "workspace_retries", "smem_contigs", "fallback_contigs",
+                                                "guard_trips", "refined_groups", "host_syncs")},
         }
         print(json.dumps(line))
     eng.close()

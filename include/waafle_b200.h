@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WFL_ABI_VERSION 1
+#define WFL_ABI_VERSION 2
 #define WFL_MAX_SYSTEMS 32
 
 typedef struct wfl_engine wfl_engine;
@@ -85,6 +85,30 @@ typedef struct {
     const int8_t  *locus_strand;   /* [n_loci] first byte of the GFF strand column */
 } wfl_batch;
 
+/* The same batch in the COMPACT wire format: 14 bytes per hit instead of 29 (the plugin call is bound by the
+ * host->device link).  What is dropped is what the engine does not need per hit: scov_modified is used for exactly
+ * one comparison (waafle_orgscorer.py:362), which the host applies while packing (utils.py:214-229 already computes
+ * the value) and ships as one bit; the strand is one bit (utils.py:214); node indices and query coordinates fit 14 and
+ * 16 bits.  Usable when the taxonomy has <= 16384 nodes, every query coordinate is <= 65535 and n_systems <= 8
+ * (the engine rejects the batch otherwise).  Results are identical to the wide format's. */
+typedef struct {
+    int64_t n_contigs, n_hits, n_loci;
+    const int64_t *hit_off;        /* [n_contigs+1] */
+    const int64_t *locus_off;      /* [n_contigs+1] */
+    const uint16_t *hit_qstart16;  /* [n_hits] Hit.qstart                                              */
+    const uint16_t *hit_qend16;    /* [n_hits] Hit.qend                                                */
+    const uint16_t *hit_tax16;     /* [n_hits] bits 0-13 node index of Hit.taxon, bit 14 sstrand == '-',
+                                      bit 15 scov_modified >= --min-scov                              */
+    const double   *hit_score;     /* [n_hits] Hit.waafle_score                                        */
+    const uint8_t  *hit_sysmask8;  /* [n_hits] bit s: hit annotates system s; NULL if n_systems == 0   */
+    const int32_t *locus_start;    /* [n_loci] */
+    const int32_t *locus_end;      /* [n_loci] */
+    const int8_t  *locus_strand;   /* [n_loci] */
+} wfl_packed_batch;
+#define WFL_PACKED_MAX_NODES 16384
+#define WFL_PACKED_MAX_COORD 65535
+#define WFL_PACKED_MAX_SYSTEMS 8
+
 /* call codes */
 #define WFL_CALL_UNCLASSIFIED 0
 #define WFL_CALL_NO_LGT 1
@@ -131,11 +155,13 @@ typedef struct {
     int64_t levels;             /* sum over contigs of taxonomy levels evaluated         */
     int64_t pairs_tested;       /* two-clade pairs mask-tested                           */
     int64_t pairs_scored;       /* two-clade pairs that passed the mask test             */
-    int64_t workspace_retries;  /* contigs replayed with a larger workspace              */
-    int64_t smem_contigs;       /* contigs whose whole working set stayed in shared mem  */
-    int64_t phase_cycles[12];   /* per-phase SM cycles summed over contigs (profiling aid):
-                                   0 loci+count 1 fill+annot 2 sort 3 group 4 envelope 5 weak/masks
-                                   6 one-clade 7 two-clade 8 output */
+    int64_t workspace_retries;  /* contigs replayed by the exact pipeline with a larger workspace */
+    int64_t smem_contigs;       /* contigs scored entirely in shared memory by the fused fast-path kernel */
+    int64_t fallback_contigs;   /* contigs the fast path handed to the exact pipeline (capacity or guard band) */
+    int64_t guard_trips;        /* ... of which because a rank comparison fell inside the 1e-12 guard band */
+    int64_t refined_groups;     /* gene scores recomputed in numpy's summation order inside the fast kernel */
+    int64_t host_syncs;         /* stream synchronisations inside the last call          */
+    int64_t phase_cycles[12];   /* per-phase SM cycles of the exact pipeline (only with -DWFL_PROFILE) */
     float   ms_h2d, ms_kernels, ms_d2h, ms_score_kernel;   /* CUDA-event times         */
 } wfl_stats;
 
@@ -153,18 +179,37 @@ int  wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent,
                       const int32_t *depth, const int32_t *leaf_count, const uint8_t *listed,
                       int32_t root_idx, int32_t unknown_idx);
 
-/* Host buffers in, host buffers out: H2D + kernels + D2H (the plugin call; bench "e2e"). */
+/* Host buffers in, host buffers out: H2D + kernels + D2H (the plugin call; bench "e2e").  `out` may be NULL: the
+ * results then stay on the device (wfl_pack_results / wfl_download_results fetch them). */
 int  wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out);
+int  wfl_score_packed(wfl_engine *e, const wfl_packed_batch *in, wfl_results *out);
 
 /* Split form for device-resident timing (bench "value"): upload once, run many, download. */
 int  wfl_upload_batch(wfl_engine *e, const wfl_batch *in);
+int  wfl_upload_packed(wfl_engine *e, const wfl_packed_batch *in);
 int  wfl_run_resident(wfl_engine *e);
 int  wfl_download_results(wfl_engine *e, wfl_results *out);
 
 int  wfl_get_stats(const wfl_engine *e, wfl_stats *out);
-/* Tuning knobs (all optional): threads per CTA, dynamic shared memory bytes per CTA,
- * CTAs per SM.  0 keeps the default. */
-int  wfl_configure(wfl_engine *e, int threads, int smem_bytes, int ctas_per_sm);
+/* Tuning / test knobs by name (all optional; defaults are the measured best on B200):
+ *   "exact"        1: every contig through the exact pipeline (numpy-pairwise gene scores, bit-exact crit / rank);
+ *                  0 (default): fused fast-path kernel with guard bands, exact pipeline for what it hands back
+ *   "fast_kcap" / "fast_tcap" / "fast_ncap"   capacities of the fast kernel's shared-memory slice (records per
+ *                  locus, clades and groups per level); 0 = choose from the batch
+ *   "pool_mb"      workspace pool of the exact pipeline; "chunk_mb" H2D chunk of the plugin call; "streams" 1|2;
+ *   "k2_cap"       group-list capacity of the exact pipeline (test hook for its overflow path). */
+int  wfl_set_option(wfl_engine *e, const char *name, int64_t value);
+
+/* Multi-GPU gather support: the compacted results of the last run, packed by one kernel into ONE
+ * device buffer on the engine's stream, ready for a single NCCL gather.  Layout: 8 int64 header {n_contigs, n_loci,
+ * n_systems, n_members, 0...}, then the wfl_results arrays in declaration order, each section 16-byte aligned
+ * (wfl_packed_results_layout gives the offsets for given sizes).  The pointer stays valid until the next call on
+ * this engine; `stream` is the cudaStream_t the buffer is ordered on. */
+int  wfl_pack_results(wfl_engine *e, void **dev_ptr, int64_t *bytes, void **stream);
+/* byte offsets of the 18 sections {call, direction, lifts, clade1, clade2, lca, best1, best2, crit, rank, member_off,
+ * n_members_a, members, synteny, locus_flags, ann_winner, call_counts, call_index} and the total size */
+int64_t wfl_packed_results_layout(int64_t n_contigs, int64_t n_loci, int32_t n_systems, int64_t n_members,
+                                  int64_t offsets[18]);
 
 /* Page-locked host memory for callers without a CUDA binding of their own (pinned buffers make the
  * H2D / D2H copies of wfl_score_batch asynchronous and ~2x faster).  Free with wfl_host_free. */

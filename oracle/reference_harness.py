@@ -2,9 +2,11 @@
 TEST INFRASTRUCTURE ONLY -- drives the UNMODIFIED reference classes in-process.
 
 Imports `waafle.utils` / `waafle.waafle_orgscorer` from /root/reference (read-only, present
-only in the build container, never on the GPU box) and replays the body of the reference's
-`main()` (waafle/waafle_orgscorer.py:900-960) on text inputs, returning one plain record
-per contig.  Used to (a) pin oracle/orgscorer_oracle.py and (b) generate tests/golden/.
+only in the build container) or, on the GPU box, from oracle/_ref/ (the same files, pip-installed
+there by oracle/build_ref.py; git-ignored) and replays the body of the reference's `main()`
+(waafle/waafle_orgscorer.py:900-960) on text inputs, returning one plain record per contig.
+Used to (a) pin oracle/orgscorer_oracle.py, (b) generate tests/golden/ and (c) time the real
+reference on the host cores beside the GPU numbers (`time_reference_sharded`, bench.py).
 
 Determinism: the reference iterates a Python set of clade names (OS:587, OS:603-607), so
 exact rank ties depend on PYTHONHASHSEED.  `CanonContig` only changes the *iteration order*
@@ -14,8 +16,12 @@ of `Contig.clades` to ascending name; every line of reference log
 import argparse
 import os
 import sys
+import time
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("WAAFLE_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "waafle")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref")   # installed copy of the unmodified reference (oracle/build_ref.py)
 
 
 def available():
@@ -63,9 +69,12 @@ def make_args(**over):
     return argparse.Namespace(**d)
 
 
-def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True):
-    """Replay OS:900-960; returns {contig_name: record} in FASTA order."""
+def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True, timers=None):
+    """Replay OS:900-960; returns {contig_name: record} in FASTA order.  `timers` (dict) receives the seconds spent
+    inside the engine region OS:952-960 ("engine") and in the whole replay including the parsers ("total")."""
     wu, wo = _import()
+    t_total = time.perf_counter()
+    t_engine = 0.0
 
     if canonical:
         class CanonContig(wo.Contig):
@@ -94,14 +103,20 @@ def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True):
         if name not in cs:
             continue
         C = cs[name]
+        t0 = time.perf_counter()
         C.attach_hits(hits)
         C.update_gene_scores()
-        level0[name] = {k: [float(x) for x in v] for k, v in C.gene_scores.items()}
+        if timers is None:
+            level0[name] = {k: [float(x) for x in v] for k, v in C.gene_scores.items()}
         if args.jump_taxonomy is not None:
             for _ in range(args.jump_taxonomy):
                 C.raise_taxonomy(tax)
         if not all([L.ignore for L in C.loci]):
             wo.evaluate_contig(C, tax, None, args)
+        t_engine += time.perf_counter() - t0
+    if timers is not None:
+        timers["engine"] = t_engine
+        timers["total"] = time.perf_counter() - t_total
     out = {}
     for name, C in cs.items():
         b1, b2 = C.best_one, C.best_two
@@ -124,3 +139,29 @@ def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True):
             rec.update(call="unclassified")
         out[name] = rec
     return out
+
+
+def _shard_worker(job):
+    files, flags = job
+    timers = {}
+    out = run_reference(files["contigs"], files["blastout"], files["gff"], files["taxonomy"], make_args(**flags),
+                        canonical=False, timers=timers)
+    calls = [0, 0, 0]
+    for r in out.values():
+        calls[{"lgt": 0, "no_lgt": 1, "unclassified": 2}[r["call"]]] += 1
+    return timers["engine"], timers["total"], calls
+
+
+def time_reference_sharded(shard_files, flags=None):
+    """The UNMODIFIED reference on `shard_files` (one dict of text-file paths per process; contigs are independent and
+    the inputs are grouped by contig, UT:255-270, 341-355).  Returns (wall seconds, max engine-only seconds over the
+    processes, summed call counts)."""
+    import multiprocessing as mp
+    jobs = [(f, flags or {}) for f in shard_files]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(jobs)) as pool:
+        res = pool.map(_shard_worker, jobs)
+    wall = time.perf_counter() - t0
+    calls = [sum(r[2][i] for r in res) for i in range(3)]
+    return wall, max(r[0] for r in res), max(r[1] for r in res), calls

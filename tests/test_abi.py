@@ -17,7 +17,7 @@ def test_library_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), "missing export: " + name
     assert sorted(engine.EXPORTS) == declared
-    assert engine.load_library().wfl_abi_version() == 1
+    assert engine.load_library().wfl_abi_version() == engine.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback_without_gpu():

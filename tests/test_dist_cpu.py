@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     P = OrgscorerParams(n_systems=1)
     shard, c0, c1 = wdist.local_shard(batch, rank, world)
     res = oracle.score_batch(P.as_dict(), tax.tables(), shard.arrays())
-    full = wdist.gather_results(res, shard, int(batch.hit_off[c0]), dist)
+    full = wdist.gather_results(res, int(batch.hit_off[c0]), dist)
     if rank == 0:
         ref = oracle.score_batch(P.as_dict(), tax.tables(), batch.arrays())
         q.put(helpers.compare_results(ref, full))

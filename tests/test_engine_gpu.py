@@ -1,8 +1,9 @@
 """GPU parity tests proper: the CUDA engine, called through the C ABI, against the oracle.
 
-Bar: every integer / byte / index output bit-exact; crit and rank bit-exact as well (the engine
-reproduces numpy's pairwise summation order), which is stricter than the 1e-12 relative
-tolerance BASELINE.json's north_star allows.
+Two modes, both run by every comparison helper here:
+  * default (fused fast-path kernel with guard bands, exact pipeline for what it hands back): every integer / byte /
+    index output bit-exact, crit and rank within SCORE_RTOL = 1e-12 relative (BASELINE.json north_star tolerance);
+  * exact (`set_option("exact", 1)`, the numpy-pairwise pipeline): crit and rank bit-exact as well.
 """
 import numpy as np
 import pytest
@@ -13,6 +14,8 @@ from oracle import orgscorer_oracle as oracle
 from oracle.validate_against_reference import FLAG_SETS, compare_records, records_from_results
 
 pytestmark = pytest.mark.gpu
+SCORE_RTOL = 1e-12
+MODES = (("fast", 0, SCORE_RTOL), ("exact", 1, 0.0))
 
 DEMO = helpers.load_json("demo_records.json.gz")
 SYNTH = helpers.load_json("synth_records.json.gz")
@@ -24,13 +27,24 @@ def run_engine(engine, P, tax, batch):
     return engine.score_batch(batch)
 
 
+def check_vs_ref(engine, P, tax, batch, ref, what=None):
+    """Both engine modes against reference results `ref`; leaves the engine in the default (fast) mode."""
+    got = None
+    try:
+        for mode, exact, rtol in MODES:
+            engine.set_option("exact", exact)
+            got = run_engine(engine, P, tax, batch)
+            diffs = helpers.compare_results(ref, got, score_rtol=rtol)
+            assert not diffs, (mode, what, diffs[:4])
+    finally:
+        engine.set_option("exact", 0)
+    return got
+
+
 def check_vs_oracle(engine, batch, tax, flags, n_systems):
     P = helpers.params_for(flags, n_systems)
-    got = run_engine(engine, P, tax, batch)
     ref = oracle.score_batch(P.as_dict(), tax.tables(), batch.arrays())
-    diffs = helpers.compare_results(ref, got)
-    assert not diffs, (flags, diffs[:4])
-    return got
+    return check_vs_ref(engine, P, tax, batch, ref, flags)
 
 
 @pytest.mark.parametrize("gff", ["genecaller", "prodigal"])
@@ -39,10 +53,13 @@ def test_demo_golden_records_through_c_abi(engine, tmp_path, gff):
     batch, loci, hits, tax = helpers.frontend_load(helpers.demo_files(tmp_path, gff == "prodigal"))
     for fi, flags in enumerate(DEMO["flag_sets"]):
         P = helpers.params_for(flags, len(hits.systems))
-        res = run_engine(engine, P, tax, batch)
-        recs = records_from_results(batch, loci, hits, tax, res)
-        diffs = compare_records(helpers.decode_golden(DEMO["records"]["{}:{}".format(gff, fi)]), recs)
-        assert not diffs, (flags, diffs[:4])
+        for mode, exact, rtol in MODES:
+            engine.set_option("exact", exact)
+            res = run_engine(engine, P, tax, batch)
+            recs = records_from_results(batch, loci, hits, tax, res)
+            diffs = compare_records(helpers.decode_golden(DEMO["records"]["{}:{}".format(gff, fi)]), recs, exact_scores=(rtol == 0.0), rtol=SCORE_RTOL)
+            assert not diffs, (mode, flags, diffs[:4])
+    engine.set_option("exact", 0)
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg5", "cfg4"])
@@ -54,10 +71,13 @@ def test_synthetic_golden_records_through_c_abi(engine, tmp_path, name):
     batch, loci, hits, tax = helpers.frontend_load(data.write_files(str(tmp_path), name))
     for fi, golden in entry["records"].items():
         P = helpers.params_for(SYNTH["flag_sets"][int(fi)], len(hits.systems))
-        res = run_engine(engine, P, tax, batch)
-        recs = records_from_results(batch, loci, hits, tax, res)
-        diffs = compare_records(helpers.decode_golden(golden), recs)
-        assert not diffs, (name, fi, diffs[:4])
+        for mode, exact, rtol in MODES:
+            engine.set_option("exact", exact)
+            res = run_engine(engine, P, tax, batch)
+            recs = records_from_results(batch, loci, hits, tax, res)
+            diffs = compare_records(helpers.decode_golden(golden), recs, exact_scores=(rtol == 0.0), rtol=SCORE_RTOL)
+            assert not diffs, (mode, name, fi, diffs[:4])
+    engine.set_option("exact", 0)
 
 
 @pytest.mark.parametrize("config,n,seed", [("cfg2", 400, 21), ("cfg3", 150, 22), ("cfg5", 150, 23)])
@@ -87,10 +107,13 @@ def test_adversarial_vs_oracle(engine, name):
     for flags in helpers.ADVERSARIAL_FLAGS:
         got = check_vs_oracle(engine, batch, tax, flags, 1)
     if name == "knife_edge":
-        # rounding alone splits this fixture between calls (finding 2)
+        # rounding alone splits this fixture between calls (finding 2): the fast path must
+        # recompute those gene scores in numpy's summation order (guard band) to get every call right
         P = helpers.params_for({}, 1)
         got = run_engine(engine, P, tax, batch)
         assert got["call_counts"][0] > 100 and got["call_counts"][1] > 100
+        st = engine.stats()
+        assert st["refined_groups"] > 500 and st["smem_contigs"] + st["fallback_contigs"] == batch.n_contigs
 
 
 def test_min_overlap_zero_python_slice_quirk(engine):
@@ -108,6 +131,7 @@ def test_level0_gene_scores_bit_exact(engine):
     batch = data.to_batch(tax)
     P = helpers.params_for(dict(weak_loci="penalize"), 0)
     ref = oracle.score_batch(P.as_dict(), tax.tables(), batch.arrays(), want_gene_scores=True)
+    engine.set_option("exact", 1)   # the dump comes from the exact pipeline
     engine.set_params(P)
     engine.set_taxonomy(tax)
     engine.upload(batch)
@@ -121,6 +145,7 @@ def test_level0_gene_scores_bit_exact(engine):
         # entries the engine does not list are loci without a matched hit: score 0
         assert all(v == 0.0 for k, v in want.items() if k not in got)
         n_checked += len(got)
+    engine.set_option("exact", 0)
     assert n_checked > 1000
 
 
@@ -158,6 +183,9 @@ def test_full_size_properties(engine):
     P = helpers.params_for({}, 0)
     a = run_engine(engine, P, tax, batch)
     b = engine.score_batch(batch)
+    st = engine.stats()
+    assert st["smem_contigs"] > 0.9 * batch.n_contigs   # the fused shared-memory kernel is the path that ran
+    assert st["smem_contigs"] + st["fallback_contigs"] == batch.n_contigs
     for k in helpers.EXACT_FIELDS + ["crit", "rank"]:
         assert np.array_equal(a[k], b[k]), k
     n = batch.n_contigs
@@ -176,7 +204,11 @@ def test_full_size_properties(engine):
         sub = batch.slice(int(c0), int(c0) + 25)
         ref = oracle.score_batch(P.as_dict(), tax.tables(), sub.arrays())
         got = engine.score_batch(sub)
-        assert not helpers.compare_results(ref, got)
+        assert not helpers.compare_results(ref, got, score_rtol=SCORE_RTOL)
+    # (f) the compact wire format (14 B/hit) gives the same bytes as the wide one
+    c = engine.score_batch(batch.to_packed(P.min_scov))
+    for k in helpers.EXACT_FIELDS + ["crit", "rank"]:
+        assert np.array_equal(a[k], c[k]), k
 
 
 @pytest.mark.parametrize("config,n,flags", [
@@ -194,61 +226,35 @@ def test_full_size_bit_exact_vs_c_oracle(engine, config, n, flags):
     tax = data.taxonomy()
     batch = data.to_batch(tax)
     P = helpers.params_for(flags, 1 if config == "cfg5" else 0)
-    got = run_engine(engine, P, tax, batch)
     ref = c_oracle.score_batch(P, tax, batch)
-    diffs = helpers.compare_results(ref, got)
-    assert not diffs, diffs[:4]
+    got = check_vs_ref(engine, P, tax, batch, ref, (config, flags))
     assert got["call_counts"].sum() == batch.n_contigs
+    if batch.can_pack(len(tax.tables()["parent"]), P.n_systems):
+        got = engine.score_batch(batch.to_packed(P.min_scov))
+        assert not helpers.compare_results(ref, got, score_rtol=SCORE_RTOL), "packed"
 
 
-def test_tree_walk_gene_scores_bit_exact(monkeypatch):
-    """WFL_K2=tree: the gene-score sums by tree walk with constant-subtree skipping (experimental,
-    slower on B200) must reproduce the flat leaf-plan walk bit for bit."""
+def test_fast_path_capacity_fallbacks():
+    """Tiny slice capacities: most contigs overflow the fast kernel's shared-memory slice and are handed to the exact
+    pipeline; results do not change (calls bit-exact, scores within tolerance)."""
     from waafle_b200 import synth
     from waafle_b200.engine import Engine
-    data = synth.generate_config("cfg2", n_contigs=500, seed=63)
+    data = synth.generate_config("cfg3", n_contigs=600, seed=63, annotations=True)
     tax = data.taxonomy()
     batch = data.to_batch(tax)
-    P = helpers.params_for({}, 0)
-    outs = []
-    # "global": K2 over the sorted global group list (default); "contig": K2 per contig; "tree": per contig, tree walk
-    for k2 in ("global", "contig", "tree"):
-        monkeypatch.setenv("WFL_K2", k2)
+    P = helpers.params_for(dict(weak_loci="assign-unknown", range=0.3), 1)
+    ref = c_oracle.score_batch(P, tax, batch)
+    for opts in (dict(fast_kcap=64, fast_tcap=64, fast_ncap=96), dict(fast_tcap=64), dict(fast_ncap=96), {}):
         eng = Engine(0, P, tax)
-        outs.append(eng.score_batch(batch))
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        got = eng.score_batch(batch)
+        st = eng.stats()
         eng.close()
-    assert not helpers.compare_results(outs[0], outs[1])
-    assert not helpers.compare_results(outs[0], outs[2])
-    batch2, tax2 = helpers.adversarial_batches()["knife_edge"]
-    eng = Engine(0, helpers.params_for({}, 1), tax2)
-    got = eng.score_batch(batch2)
-    eng.close()
-    ref = oracle.score_batch(helpers.params_for({}, 1).as_dict(), tax2.tables(), batch2.arrays())
-    assert not helpers.compare_results(ref, got)
-
-
-@pytest.mark.parametrize("mode", ["v2", "v1"])
-def test_alternate_kernels_stay_bit_exact(mode, monkeypatch):
-    """The monolithic warp kernel (v2: also the replay path for contigs that outgrow the pipeline's
-    workspace) and the first CTA-per-contig kernel (v1) are selectable with WFL_KERNEL and must give
-    the same bytes as the default multi-kernel pipeline."""
-    from waafle_b200 import synth
-    from waafle_b200.engine import Engine
-    data = synth.generate_config("cfg3", n_contigs=300, seed=61, annotations=True)
-    tax = data.taxonomy()
-    batch = data.to_batch(tax)
-    outs = {}
-    for m in ("pipe", mode):
-        monkeypatch.setenv("WFL_KERNEL", m)
-        for flags in ({}, dict(weak_loci="assign-unknown", range=0.3), dict(jump_taxonomy=1)):
-            P = helpers.params_for(flags, 1)
-            eng = Engine(0, P, tax)
-            outs.setdefault(m, []).append(eng.score_batch(batch))
-            eng.close()
-    for a, b in zip(outs["pipe"], outs[mode]):
-        assert not helpers.compare_results(a, b)
-    ref = oracle.score_batch(helpers.params_for({}, 1).as_dict(), tax.tables(), batch.arrays())
-    assert not helpers.compare_results(ref, outs[mode][0])
+        assert not helpers.compare_results(ref, got, score_rtol=SCORE_RTOL), opts
+        assert st["smem_contigs"] + st["fallback_contigs"] == batch.n_contigs
+        if opts:
+            assert st["fallback_contigs"] > 0, opts
 
 
 def test_many_small_chunks_on_two_streams(monkeypatch):
@@ -267,20 +273,22 @@ def test_many_small_chunks_on_two_streams(monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        eng = Engine(0, P, tax)
-        got = eng.score_batch(batch)
-        again = eng.score_batch(batch)
-        st = eng.stats()
-        eng.close()
-        assert not helpers.compare_results(ref, got), env
-        assert not helpers.compare_results(ref, again), env
-        if env.get("WFL_CHUNK_MB") == "1":
-            assert st["kernel_launches"] > 20 * 20   # many chunks really ran
+        for exact in (0, 1):
+            eng = Engine(0, P, tax)
+            eng.set_option("exact", exact)
+            got = eng.score_batch(batch)
+            again = eng.score_batch(batch)
+            st = eng.stats()
+            eng.close()
+            assert not helpers.compare_results(ref, got, score_rtol=0.0 if exact else SCORE_RTOL), env
+            assert not helpers.compare_results(ref, again, score_rtol=0.0 if exact else SCORE_RTOL), env
+            if env.get("WFL_CHUNK_MB") == "1":
+                assert st["kernel_launches"] > (20 * 20 if exact else 20)   # many chunks really ran
 
 
 def test_group_list_overflow_replays(monkeypatch):
-    """A K2 group list that is far too small (WFL_K2_CAP): contigs that do not fit are replayed by the warp
-    kernel, the list never holds unwritten items, and the results do not change."""
+    """Exact pipeline with a K2 group list that is far too small (WFL_K2_CAP): contigs that do not fit are replayed
+    with a larger list, the list never holds unwritten items, and the results do not change."""
     from waafle_b200 import synth
     from waafle_b200.engine import Engine
     data = synth.generate_config("cfg2", n_contigs=600, seed=77)
@@ -291,6 +299,7 @@ def test_group_list_overflow_replays(monkeypatch):
     for cap in ("3000", "1"):
         monkeypatch.setenv("WFL_K2_CAP", cap)
         eng = Engine(0, P, tax)
+        eng.set_option("exact", 1)
         got = eng.score_batch(batch)
         st = eng.stats()
         eng.close()
@@ -299,8 +308,8 @@ def test_group_list_overflow_replays(monkeypatch):
 
 
 def test_small_workspace_pool_replays(monkeypatch):
-    """A pool too small for a long contig: it is replayed by the monolithic kernel
-    (workspace_retries > 0) and the results do not change (members included)."""
+    """A workspace pool too small for a long contig: it is replayed with a larger pool (workspace_retries > 0)
+    and the results do not change (members included)."""
     from waafle_b200 import synth
     from waafle_b200.engine import Engine
     data = synth.generate_config("cfg4", n_contigs=4, seed=62)

@@ -1,6 +1,6 @@
 """Profiling driver: one resident batch, a few runs; prints per-phase cycle shares.
 
-usage: python tools/prof_run.py [workload] [contigs] [runs] [threads] [smem] [ctas_per_sm]
+usage: python tools/prof_run.py [workload] [contigs] [runs] [name=value engine options ...]
 """
 import os
 import sys
@@ -10,8 +10,7 @@ from waafle_b200 import synth                     # noqa: E402
 from waafle_b200.engine import Engine             # noqa: E402
 from waafle_b200.params import OrgscorerParams    # noqa: E402
 
-# pipeline mode fills slots 0 (prepare), 3 (scores), 5 (one-clade), 6 (two-clade + lift);
-# the monolithic kernels (WFL_KERNEL=v2 / v1) fill all nine
+# per-phase cycles of the exact pipeline; only filled when the library is built with -DWFL_PROFILE
 PHASES = ["prepare/match+fill", "clade table", "regroup", "scores (K2..masks)", "weak/masks", "one-clade",
           "two-clade(+lift)", "lift", "output"]
 
@@ -21,13 +20,14 @@ def main():
     workload = a[0] if len(a) > 0 else "cfg2"
     n = int(a[1]) if len(a) > 1 else 5000
     runs = int(a[2]) if len(a) > 2 else 3
-    cfg = [int(x) for x in a[3:6]] + [0] * (3 - len(a[3:6]))
+    opts = [x.split("=") for x in a[3:]]
     data = synth.generate_config(workload, n_contigs=n, seed=1000)
     tax = data.taxonomy()
     batch = data.to_batch(tax)
     P = OrgscorerParams(n_systems=1 if batch.hit_sysmask is not None else 0)
     eng = Engine(0, P, tax)
-    eng.configure(*cfg)
+    for k, v in opts:
+        eng.set_option(k, int(v))
     eng.upload(batch)
     for _ in range(runs):
         eng.run_resident()

@@ -28,10 +28,10 @@ struct wfl_engine {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_join = nullptr;
-    int n_slots = 2;                     // plugin call: sub-batches alternate between two compute streams
+    int n_slots = 2;                     // sub-batches alternate between two compute streams
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> chunk_ev;
-    size_t chunk_bytes = size_t(96) << 20;   // H2D chunk size of the pipelined plugin call (measured best: profiles/README.md)
+    size_t chunk_bytes = size_t(48) << 20;   // H2D chunk size of the pipelined plugin call
     std::string err;
     bool have_params = false, have_tax = false, have_batch = false, have_results = false;
     DevParams P{};
@@ -40,29 +40,25 @@ struct wfl_engine {
     DevOut o{};
     int64_t n = 0, nh = 0, nl = 0;
     int S = 0;
-    // knobs
-    int threads = 32, smem_bytes = 10 * 1024, ctas_per_sm = 12;
-    size_t slab_bytes = 256 * 1024;
-    // device buffers (grow-only)
-    Buf tx[4], in[12], out[18], slab, ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data, plan_tree;
-    int plan_nmax = 0;
-    // multi-kernel pipeline state
-    int mode = 2;                       // 0: v1 CTA-per-contig, 1: v2 monolithic warp kernel, 2: pipeline
-    int tax_max_depth = 0;
-    bool use_tree = false;              // WFL_K2=tree: K2 by tree walk with constant-subtree skipping (parity-tested,
-                                        // but slower than the flat leaf plan on B200: more local-memory state)
+    bool packed = false;                 // the resident batch is in the compact wire format
+    // options (wfl_set_option / environment)
+    bool exact = false;                  // every contig through the exact pipeline
+    int fast_kcap = 0, fast_tcap = 0, fast_ncap = 0;
     size_t pipe_pool_bytes = size_t(8192) << 20;
+    size_t k2_cap_override = 0;
+    bool chunk_fixed = false;
+    // device buffers (grow-only)
+    Buf tx[4], anc, in[12], out[18], ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
+    Buf fb_list, fast_scratch, fast_wq, blob, status_tmp;
+    int plan_nmax = 0;
+    int tax_max_depth = 0, anc_rows = 0;
+    FastCfg fcfg{};
+    int fast_grid = 0;
+    // exact pipeline state
     Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2], k2_desc[2], k2_order[2], k2_keys[2], k2_meta[2];
-    size_t k2_cap_override = 0;         // WFL_K2_CAP: descriptor capacity per sub-batch (test hook for the overflow path)
-    bool k2_global = true;              // WFL_K2=contig: K2 per contig (wfl_pipe_scores) instead of the sorted global group list
     std::vector<int64_t> h_hit_off, h_locus_off;
     std::vector<int64_t> chunks;         // contig boundaries of the sub-batches of the current batch
     bool chunks_streamed = false;        // their H2D copies are in flight on copy_stream (plugin call)
-    int resident_split = 1;              // WFL_SPLIT > 1: sub-batches of a resident batch on both compute streams (measured
-                                         // slower: kernels of different phases then share the SMs and their instruction caches)
-    bool chunk_fixed = false;            // WFL_CHUNK_MB given: use it as is
-    double chunk_shrink = 1.0;           // < 1: geometric tail of the streaming schedule, each chunk >= shrink * its
-                                         // predecessor (WFL_CHUNK_SHRINK; measured no better than equal chunks)
     wfl_stats stats{};
     int64_t members_total = 0;
 };
@@ -170,39 +166,6 @@ void host_build_plan(int n, std::vector<uint16_t> &data, PlanEntry &pe) {
 }
 
 
-// Distinct node sizes of the split tree of an n-element sum, ascending, children by index.
-void host_build_tree(int n, std::vector<TreeEntry> &data, PlanEntry &pe) {
-    std::vector<int> sizes;
-    std::vector<int> todo{n};
-    while (!todo.empty()) {
-        int m = todo.back();
-        todo.pop_back();
-        if (std::find(sizes.begin(), sizes.end(), m) != sizes.end()) continue;
-        sizes.push_back(m);
-        if (m > 128) {
-            int n2 = m / 2;
-            n2 -= n2 % 8;
-            todo.push_back(n2);
-            todo.push_back(m - n2);
-        }
-    }
-    std::sort(sizes.begin(), sizes.end());
-    pe.toff = (uint32_t)data.size();
-    pe.nsz = (uint32_t)sizes.size();
-    for (int m : sizes) {
-        TreeEntry t;
-        t.size = (uint16_t)m;
-        t.li = t.ri = 255;
-        if (m > 128) {
-            int n2 = m / 2;
-            n2 -= n2 % 8;
-            t.li = (uint8_t)(std::find(sizes.begin(), sizes.end(), n2) - sizes.begin());
-            t.ri = (uint8_t)(std::find(sizes.begin(), sizes.end(), m - n2) - sizes.begin());
-        }
-        data.push_back(t);
-    }
-}
-
 // Leaf plans for every gene length up to `want` (capped): built once, kept on the device.
 int ensure_plan_table(wfl_engine *e, int want) {
     const int cap = 16384;
@@ -212,54 +175,14 @@ int ensure_plan_table(wfl_engine *e, int want) {
     std::vector<uint16_t> data;
     data.reserve((size_t)want * want / 150 + 1024);
     index[0] = PlanEntry{0, 0, 0};
-    std::vector<TreeEntry> tdata;
-    tdata.reserve((size_t)want * 18);
-    index[0].toff = index[0].nsz = 0;
-    for (int n = 1; n <= want; ++n) {
-        host_build_plan(n, data, index[n]);
-        host_build_tree(n, tdata, index[n]);
-    }
+    for (int n = 1; n <= want; ++n) host_build_plan(n, data, index[n]);
     const PlanEntry *di;
     const uint16_t *dd;
     int rc;
     if ((rc = upload(e, e->plan_index, index.data(), index.size(), &di))) return rc;
     if ((rc = upload(e, e->plan_data, data.data(), data.size(), &dd))) return rc;
-    const TreeEntry *dt;
-    if ((rc = upload(e, e->plan_tree, tdata.data(), tdata.size(), &dt))) return rc;
     CU(cudaStreamSynchronize(e->stream));
     e->plan_nmax = want;
-    return WFL_OK;
-}
-
-int check_batch(wfl_engine *e, const wfl_batch *in) {
-    if (!in || in->n_contigs < 0 || in->n_hits < 0 || in->n_loci < 0) {
-        set_err(e, "bad batch sizes");
-        return WFL_ERR_ARG;
-    }
-    if (in->n_hits >= (1ll << 31) || in->n_loci >= (1ll << 31) || in->n_contigs >= (1ll << 31)) {
-        set_err(e, "batch too large: contigs, hits and loci must each be < 2^31 per batch");
-        return WFL_ERR_ARG;
-    }
-    if (!in->hit_off || !in->locus_off || (in->n_hits && (!in->hit_qstart || !in->hit_qend ||
-        !in->hit_taxon || !in->hit_score || !in->hit_scov || !in->hit_strand)) ||
-        (in->n_loci && (!in->locus_start || !in->locus_end || !in->locus_strand))) {
-        set_err(e, "null array in batch");
-        return WFL_ERR_ARG;
-    }
-    if (e->P.p.n_systems > 0 && in->n_hits && !in->hit_sysmask) {
-        set_err(e, "n_systems > 0 but hit_sysmask is null");
-        return WFL_ERR_ARG;
-    }
-    if (in->hit_off[0] != 0 || in->locus_off[0] != 0 || in->hit_off[in->n_contigs] != in->n_hits ||
-        in->locus_off[in->n_contigs] != in->n_loci) {
-        set_err(e, "CSR offsets do not span the hit / locus arrays");
-        return WFL_ERR_ARG;
-    }
-    for (int64_t c = 0; c < in->n_contigs; ++c)
-        if (in->hit_off[c + 1] < in->hit_off[c] || in->locus_off[c + 1] < in->locus_off[c]) {
-            set_err(e, "CSR offsets are not monotone at contig %lld", (long long)c);
-            return WFL_ERR_ARG;
-        }
     return WFL_OK;
 }
 
@@ -291,53 +214,147 @@ int alloc_outputs(wfl_engine *e) {
     return rc;
 }
 
-int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all);
+// One host-side description of a batch in either wire format.
+struct HostBatch {
+    int64_t n = 0, nh = 0, nl = 0;
+    const int64_t *hit_off = nullptr, *locus_off = nullptr;
+    const int32_t *locus_start = nullptr, *locus_end = nullptr;
+    const int8_t *locus_strand = nullptr;
+    bool packed = false;
+    // hit columns: (source pointer, element size); wide: qstart qend taxon score scov strand sysmask,
+    // packed: qstart16 qend16 tax16 score sysmask8
+    const void *col[7] = {};
+    int esz[7] = {};
+    int ncol = 0;
+};
+
+HostBatch host_batch(const wfl_batch *in, int S) {
+    HostBatch h;
+    h.n = in->n_contigs; h.nh = in->n_hits; h.nl = in->n_loci;
+    h.hit_off = in->hit_off; h.locus_off = in->locus_off;
+    h.locus_start = in->locus_start; h.locus_end = in->locus_end; h.locus_strand = in->locus_strand;
+    const void *c[7] = {in->hit_qstart, in->hit_qend, in->hit_taxon, in->hit_score, in->hit_scov, in->hit_strand,
+                        S > 0 ? in->hit_sysmask : nullptr};
+    const int z[7] = {4, 4, 4, 8, 8, 1, 4};
+    for (int i = 0; i < 7; ++i) { h.col[i] = c[i]; h.esz[i] = z[i]; }
+    h.ncol = 7;
+    return h;
+}
+
+HostBatch host_batch(const wfl_packed_batch *in, int S) {
+    HostBatch h;
+    h.packed = true;
+    h.n = in->n_contigs; h.nh = in->n_hits; h.nl = in->n_loci;
+    h.hit_off = in->hit_off; h.locus_off = in->locus_off;
+    h.locus_start = in->locus_start; h.locus_end = in->locus_end; h.locus_strand = in->locus_strand;
+    const void *c[5] = {in->hit_qstart16, in->hit_qend16, in->hit_tax16, in->hit_score, S > 0 ? in->hit_sysmask8 : nullptr};
+    const int z[5] = {2, 2, 2, 8, 1};
+    for (int i = 0; i < 5; ++i) { h.col[i] = c[i]; h.esz[i] = z[i]; }
+    h.ncol = 5;
+    return h;
+}
+
+size_t hit_row_bytes(const HostBatch &h) {
+    size_t r = 0;
+    for (int i = 0; i < h.ncol; ++i) r += h.col[i] ? (size_t)h.esz[i] : 0;
+    return r;
+}
+
+int check_host_batch(wfl_engine *e, const HostBatch &h) {
+    if (h.n < 0 || h.nh < 0 || h.nl < 0) { set_err(e, "bad batch sizes"); return WFL_ERR_ARG; }
+    if (h.nh >= (1ll << 31) || h.nl >= (1ll << 31) || h.n >= (1ll << 31)) {
+        set_err(e, "batch too large: contigs, hits and loci must each be < 2^31 per batch");
+        return WFL_ERR_ARG;
+    }
+    bool null_hit = false;
+    for (int i = 0; i < h.ncol; ++i) {
+        const bool optional = i == h.ncol - 1;   // the sysmask column
+        if (h.nh && !h.col[i] && !optional) null_hit = true;
+    }
+    if (!h.hit_off || !h.locus_off || null_hit || (h.nl && (!h.locus_start || !h.locus_end || !h.locus_strand))) {
+        set_err(e, "null array in batch");
+        return WFL_ERR_ARG;
+    }
+    if (e->P.p.n_systems > 0 && h.nh && !h.col[h.ncol - 1]) {
+        set_err(e, "n_systems > 0 but hit_sysmask is null");
+        return WFL_ERR_ARG;
+    }
+    if (h.packed && (e->tax.n_nodes > WFL_PACKED_MAX_NODES || e->P.p.n_systems > WFL_PACKED_MAX_SYSTEMS)) {
+        set_err(e, "compact wire format needs <= %d taxonomy nodes and <= %d annotation systems", WFL_PACKED_MAX_NODES,
+                WFL_PACKED_MAX_SYSTEMS);
+        return WFL_ERR_ARG;
+    }
+    if (h.hit_off[0] != 0 || h.locus_off[0] != 0 || h.hit_off[h.n] != h.nh || h.locus_off[h.n] != h.nl) {
+        set_err(e, "CSR offsets do not span the hit / locus arrays");
+        return WFL_ERR_ARG;
+    }
+    for (int64_t c = 0; c < h.n; ++c)
+        if (h.hit_off[c + 1] < h.hit_off[c] || h.locus_off[c + 1] < h.locus_off[c]) {
+            set_err(e, "CSR offsets are not monotone at contig %lld", (long long)c);
+            return WFL_ERR_ARG;
+        }
+    return WFL_OK;
+}
+
+// device pointer of hit column i of the resident batch
+void *&dev_col(wfl_engine *e, int i) { return e->in[2 + i].p; }
+
+void bind_device_batch(wfl_engine *e) {
+    DevBatch &b = e->b;
+    b.hit_qstart = b.hit_qend = b.hit_taxon = nullptr;
+    b.hit_score = b.hit_scov = nullptr;
+    b.hit_strand = nullptr;
+    b.hit_sysmask = nullptr;
+    b.hit_qstart16 = b.hit_qend16 = b.hit_tax16 = nullptr;
+    b.hit_sysmask8 = nullptr;
+    if (e->packed) {
+        b.hit_qstart16 = static_cast<const uint16_t *>(dev_col(e, 0));
+        b.hit_qend16 = static_cast<const uint16_t *>(dev_col(e, 1));
+        b.hit_tax16 = static_cast<const uint16_t *>(dev_col(e, 2));
+        b.hit_score = static_cast<const double *>(dev_col(e, 3));
+        if (e->S > 0) b.hit_sysmask8 = static_cast<const uint8_t *>(dev_col(e, 4));
+    } else {
+        b.hit_qstart = static_cast<const int32_t *>(dev_col(e, 0));
+        b.hit_qend = static_cast<const int32_t *>(dev_col(e, 1));
+        b.hit_taxon = static_cast<const int32_t *>(dev_col(e, 2));
+        b.hit_score = static_cast<const double *>(dev_col(e, 3));
+        b.hit_scov = static_cast<const double *>(dev_col(e, 4));
+        b.hit_strand = static_cast<const int8_t *>(dev_col(e, 5));
+        if (e->S > 0) b.hit_sysmask = static_cast<const uint32_t *>(dev_col(e, 6));
+    }
+    b.locus_start = static_cast<const int32_t *>(e->in[9].p);
+    b.locus_end = static_cast<const int32_t *>(e->in[10].p);
+    b.locus_strand = static_cast<const int8_t *>(e->in[11].p);
+}
 
 // Cut the batch into sub-batches of whole contigs.
-//  * pipeline mode: a sub-batch's intermediate state must fit the workspace pool;
-//  * plugin call (streaming): a sub-batch is also the unit that crosses PCIe on the copy stream while
-//    its predecessor is scored.  Byte schedule: a small first chunk (the kernels start early), full
-//    chunks, then a geometric tail s_k = shrink * s_{k-1}: the kernels are faster than the link, so as
-//    long as a chunk is not much smaller than its predecessor its copy hides the predecessor's kernels,
-//    and only the kernels of the LAST (smallest) chunk are exposed behind the end of the H2D stream.
-void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool streaming) {
+//  * exact pipeline: a sub-batch's intermediate state must fit the workspace pool;
+//  * plugin call (streaming): a sub-batch is also the unit that crosses PCIe on the copy stream while its
+//    predecessor is scored: a small first chunk (the kernels start early), then equal chunks, at most ~12 per call
+//    (every chunk costs a launch chain that ends on its slowest contig).
+void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool streaming, size_t hit_row) {
     e->chunks.clear();
     e->chunks.push_back(0);
     const int64_t n = e->n;
     if (n <= 0) return;
-    const size_t hit_row = 29 + (e->S > 0 ? 4 : 0);
+    const bool pool_bound = e->exact || e->P.p.min_overlap <= 0.0;
     std::vector<size_t> target;
     if (streaming) {
-        // chunk size: 96 MB, but never more than ~12 chunks per call -- every chunk costs one pass through the
-        // per-level kernel chain (20 launches x levels, each ending on its slowest contig)
         const size_t total = (size_t)hoff[n] * hit_row;
         const size_t full = e->chunk_fixed ? e->chunk_bytes : std::max(e->chunk_bytes, total / 12 + 1);
         const size_t first = std::min(full / 4, e->chunk_bytes);
-        std::vector<size_t> tail;
-        size_t acc = 0;
-        for (size_t t = std::max<size_t>(full / 6, size_t(1) << 20); e->chunk_shrink < 0.999 && t < full && acc + t + first < total;
-             t = (size_t)((double)t / e->chunk_shrink) + 1) {
-            tail.push_back(t);
-            acc += t;
-        }
-        size_t rem = total > acc ? total - acc : 0;
+        size_t rem = total;
         target.push_back(std::min(rem, first));
         rem -= target.back();
         if (rem % full) { target.push_back(rem % full); rem -= rem % full; }   // the odd piece goes early
         for (; rem > 0; rem -= full) target.push_back(full);
-        target.insert(target.end(), tail.rbegin(), tail.rend());
     }
-    // resident batch (pipeline mode): a few sub-batches alternating between the two compute streams, so that
-    // the tail of one sub-batch's kernel chain is filled by the other's kernels
-    size_t split_hits = 0;
-    if (!streaming && e->mode == 2 && e->n_slots > 1 && e->resident_split > 1 && n >= 8192 * (int64_t)e->resident_split)
-        split_hits = (size_t)hoff[n] / (size_t)e->resident_split + 1;
     int64_t c0 = 0;
     size_t k = 0;
     while (c0 < n) {
         int64_t c1 = c0;
         size_t est = 0;
-        const size_t goal = k < target.size() ? target[k] : (target.empty() ? e->chunk_bytes : target.back());
+        const size_t goal = k < target.size() ? target[k] : (target.empty() ? ~size_t(0) : target.back());
         for (;;) {
             // workspace estimate per contig (records + table + level arrays), see wfl_pipeline.cu
             const size_t h = (size_t)(hoff[c1 + 1] - hoff[c1]), g = (size_t)(loff[c1 + 1] - loff[c1]);
@@ -345,8 +362,7 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
             ++c1;
             if (c1 >= n) break;
             if (streaming && (size_t)(hoff[c1 + 1] - hoff[c0]) * hit_row > goal) break;
-            if (!streaming && split_hits && (size_t)(hoff[c1 + 1] - hoff[c0]) > split_hits) break;
-            if (e->mode == 2 && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
+            if (pool_bound && est + 190 * (size_t)(hoff[c1 + 1] - hoff[c1]) + 9000 > e->pipe_pool_bytes) break;
         }
         e->chunks.push_back(c1);
         c0 = c1;
@@ -355,28 +371,23 @@ void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool s
 }
 
 // All H2D copies of the plugin call, chunk by chunk on the copy stream, one event per chunk.
-int issue_chunk_copies(wfl_engine *e, const wfl_batch *src) {
-    const int64_t *hoff = src->hit_off, *loff = src->locus_off;
+int issue_chunk_copies(wfl_engine *e, const HostBatch &src) {
+    const int64_t *hoff = src.hit_off, *loff = src.locus_off;
     cudaStream_t cs = e->copy_stream;
     for (size_t k = 0; k + 1 < e->chunks.size(); ++k) {
         const int64_t c0 = e->chunks[k], c1 = e->chunks[k + 1];
         const size_t h0 = (size_t)hoff[c0], h1 = (size_t)hoff[c1];
         const size_t l0 = (size_t)loff[c0], l1 = (size_t)loff[c1];
-#define CP(dst, srcp, lo, hi)                                                                         \
-    if ((hi) > (lo))                                                                                  \
-    CU(cudaMemcpyAsync(const_cast<void *>(static_cast<const void *>((dst) + (lo))), (srcp) + (lo),    \
-                       ((hi) - (lo)) * sizeof(*(srcp)), cudaMemcpyHostToDevice, cs))
-        CP(e->b.hit_qstart, src->hit_qstart, h0, h1);
-        CP(e->b.hit_qend, src->hit_qend, h0, h1);
-        CP(e->b.hit_taxon, src->hit_taxon, h0, h1);
-        CP(e->b.hit_score, src->hit_score, h0, h1);
-        CP(e->b.hit_scov, src->hit_scov, h0, h1);
-        CP(e->b.hit_strand, src->hit_strand, h0, h1);
-        if (e->S > 0) CP(e->b.hit_sysmask, src->hit_sysmask, h0, h1);
-        CP(e->b.locus_start, src->locus_start, l0, l1);
-        CP(e->b.locus_end, src->locus_end, l0, l1);
-        CP(e->b.locus_strand, src->locus_strand, l0, l1);
-#undef CP
+        for (int i = 0; i < src.ncol; ++i)
+            if (src.col[i] && h1 > h0)
+                CU(cudaMemcpyAsync(static_cast<char *>(dev_col(e, i)) + h0 * src.esz[i],
+                                   static_cast<const char *>(src.col[i]) + h0 * src.esz[i], (h1 - h0) * src.esz[i],
+                                   cudaMemcpyHostToDevice, cs));
+        if (l1 > l0) {
+            CU(cudaMemcpyAsync(static_cast<int32_t *>(e->in[9].p) + l0, src.locus_start + l0, (l1 - l0) * 4, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(static_cast<int32_t *>(e->in[10].p) + l0, src.locus_end + l0, (l1 - l0) * 4, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(static_cast<int8_t *>(e->in[11].p) + l0, src.locus_strand + l0, (l1 - l0), cudaMemcpyHostToDevice, cs));
+        }
         if (e->chunk_ev.size() <= k) {
             cudaEvent_t evn;
             CU(cudaEventCreateWithFlags(&evn, cudaEventDisableTiming));
@@ -389,8 +400,10 @@ int issue_chunk_copies(wfl_engine *e, const wfl_batch *src) {
     return WFL_OK;
 }
 
-// One sub-batch [c0, c1) through the multi-kernel pipeline (wfl_pipeline.cu).
-int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_t c1, int slot = 0) {
+// One sub-batch through the exact multi-kernel pipeline (wfl_pipeline.cu): the contig range [c0, c0 + n_work) or, with
+// `list`, the n_work contigs it names.  `hits` bounds the K2 group list; `grow` scales the capacities of a replay.
+int launch_pipeline(wfl_engine *e, DevCounters *ctr, const int *list, int64_t c0, int64_t n_work, size_t hits, int slot,
+                    size_t grow, long long dbg_contig = -1) {
     cudaStream_t stream = slot ? e->stream2 : e->stream;
     const int L = std::min(std::max(e->tax_max_depth + 1 - e->P.p.jump_taxonomy, 1), 64);
     int rc;
@@ -399,7 +412,9 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     int *lists, *cnt;
     unsigned long long *wq;
     const size_t n = (size_t)e->n;
-    if ((rc = outbuf(e, e->pipe_pool[slot], std::min<size_t>(e->pipe_pool_bytes, 200 * (size_t)e->nh + 9200 * n + 96 * (size_t)e->nl + (size_t(64) << 20)), &pool))) return rc;
+    const size_t pool_want = grow > 1 ? std::min<size_t>(std::max<size_t>(e->pipe_pool_bytes, size_t(64) << 20) * grow, size_t(64) << 30)
+                                      : std::min<size_t>(e->pipe_pool_bytes, 200 * (size_t)e->nh + 9200 * n + 96 * (size_t)e->nl + (size_t(64) << 20));
+    if ((rc = outbuf(e, e->pipe_pool[slot], std::max<size_t>(pool_want, e->pipe_pool[slot].cap), &pool))) return rc;
     if ((rc = outbuf(e, e->pipe_ctg, n, &ctg))) return rc;
     if ((rc = outbuf(e, e->pipe_lists[slot], 4 * n + 16, &lists))) return rc;
     if ((rc = outbuf(e, e->pipe_cnt[slot], 3 * 66 + 8, &cnt))) return rc;
@@ -407,15 +422,15 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
     CU(cudaMemsetAsync(cnt, 0, (3 * 66 + 8) * sizeof(int), stream));
     CU(cudaMemsetAsync(wq, 0, (6 * 66 + 8) * sizeof(unsigned long long), stream));
     PipeArgs pa{};
-    pa.b = sa.b; pa.t = sa.t; pa.o = sa.o; pa.P = sa.P; pa.ctr = sa.ctr;
-    pa.pool = pool; pa.pool_used = wq; pa.pool_cap = e->pipe_pool[slot].cap;
+    pa.b = e->b; pa.t = e->tax; pa.o = e->o; pa.P = e->P; pa.ctr = ctr;
+    pa.pool = pool; pa.pool_used = wq; pa.pool_cap = std::min<size_t>(e->pipe_pool[slot].cap, std::max<size_t>(pool_want, 16));
     pa.ctg = ctg;
-    pa.plan_nmax = sa.plan_nmax; pa.plan_index = sa.plan_index; pa.plan_data = sa.plan_data; pa.plan_tree = sa.plan_tree;
+    pa.plan_nmax = e->plan_nmax;
+    pa.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
+    pa.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
     K2Meta *k2meta = nullptr;
-    pa.k2_desc = nullptr;
-    if (e->k2_global && !e->use_tree) {
-        const size_t cap = e->k2_cap_override ? e->k2_cap_override
-                                             : (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]) * 5 / 4 + 4096;
+    {
+        const size_t cap = (e->k2_cap_override && grow <= 1) ? e->k2_cap_override : (hits * 5 / 4 + 4096) * grow;
         if ((rc = outbuf(e, e->k2_desc[slot], cap, &pa.k2_desc))) return rc;
         if ((rc = outbuf(e, e->k2_order[slot], cap, &pa.k2_order))) return rc;
         if ((rc = outbuf(e, e->k2_keys[slot], cap, &pa.k2_keys))) return rc;
@@ -423,29 +438,32 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
         pa.k2_cap = cap;
         CU(cudaMemsetAsync(k2meta, 0, 66 * sizeof(K2Meta), stream));
     }
-    pa.dbg_contig = -1;
-    int *list[4] = {lists, lists + n, lists + 2 * n, lists + 3 * n};
+    pa.dbg_contig = dbg_contig;
+    if (dbg_contig >= 0) {
+        pa.dbg_clade = static_cast<int32_t *>(e->dbg[0].p);
+        pa.dbg_locus = static_cast<int32_t *>(e->dbg[1].p);
+        pa.dbg_score = static_cast<double *>(e->dbg[2].p);
+        pa.dbg_cap = (long long)(e->dbg[0].cap / sizeof(int32_t));
+        pa.dbg_count = static_cast<long long *>(e->dbg[3].p);
+    }
+    int *lst[4] = {lists, lists + n, lists + 2 * n, lists + 3 * n};
     int *cnt_act = cnt, *cnt_two = cnt + 66, *cnt_lift = cnt + 2 * 66;
     const int grid = e->sm_count * pipe_ctas_per_sm();
     pa.wq = wq + 1;
-    pa.work_base = c0; pa.n_work = c1 - c0;
-    pa.list_act = list[0]; pa.cnt_act = &cnt_act[0];
-    launch_pipe_prepare(pa, (int)std::min<int64_t>(grid, c1 - c0), stream);
+    pa.work_base = c0; pa.n_work = n_work; pa.work_list = list;
+    pa.list_act = lst[0]; pa.cnt_act = &cnt_act[0];
+    launch_pipe_prepare(pa, (int)std::max<int64_t>(1, std::min<int64_t>(grid, n_work)), stream);
     for (int lvl = 0; lvl < L; ++lvl) {
-        pa.list_act = list[lvl & 1]; pa.cnt_act = &cnt_act[lvl];
-        pa.list_next = list[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
-        pa.list_two = list[2]; pa.cnt_two = &cnt_two[lvl];
-        pa.list_lift = list[3]; pa.cnt_lift = &cnt_lift[lvl];
-        pa.k2_meta = k2meta ? k2meta + lvl : nullptr;
+        pa.list_act = lst[lvl & 1]; pa.cnt_act = &cnt_act[lvl];
+        pa.list_next = lst[(lvl + 1) & 1]; pa.cnt_next = &cnt_act[lvl + 1];
+        pa.list_two = lst[2]; pa.cnt_two = &cnt_two[lvl];
+        pa.list_lift = lst[3]; pa.cnt_lift = &cnt_lift[lvl];
+        pa.k2_meta = k2meta + lvl;
         pa.wq = wq + 2 + 6 * lvl;
         launch_pipe_regroup(pa, grid, stream);
         pa.wq = wq + 3 + 6 * lvl;
-        if (pa.k2_desc != nullptr) {
-            launch_pipe_k2sort(pa, grid, stream);
-            launch_pipe_k2(pa, grid, stream);
-        } else {
-            launch_pipe_scores(pa, grid, stream);
-        }
+        launch_pipe_k2sort(pa, grid, stream);
+        launch_pipe_k2(pa, grid, stream);
         pa.wq = wq + 4 + 6 * lvl;
         launch_pipe_masks(pa, grid, stream);
         pa.wq = wq + 5 + 6 * lvl;
@@ -455,284 +473,84 @@ int launch_pipeline_chunk(wfl_engine *e, const ScoreArgs &sa, int64_t c0, int64_
         pa.wq = wq + 7 + 6 * lvl;
         launch_pipe_lift(pa, grid, stream);
     }
-    pa.list_act = list[L & 1]; pa.cnt_act = &cnt_act[L];
+    pa.list_act = lst[L & 1]; pa.cnt_act = &cnt_act[L];
     launch_pipe_leftover(pa, stream);
     CU(cudaGetLastError());
-    e->stats.kernel_launches += 2 + (pa.k2_desc != nullptr ? 9 : 6) * L;
+    e->stats.kernel_launches += 2 + 9 * L;
     return WFL_OK;
 }
 
-
-int run_kernels(wfl_engine *e, const wfl_batch *src = nullptr) {
-    if (!e->have_params || !e->have_tax || !e->have_batch) {
-        set_err(e, "params, taxonomy and batch must be set before running");
-        return WFL_ERR_STATE;
+// The exact pipeline over an explicit contig list (fast-path fallbacks, workspace replays), cut into sub-batches whose
+// estimated workspace fits the pool.
+int run_pipeline_list(wfl_engine *e, DevCounters *ctr, const std::vector<int> &list, size_t grow) {
+    if (list.empty()) return WFL_OK;
+    int rc;
+    int *dl;
+    if ((rc = outbuf(e, e->work, list.size(), &dl))) return rc;
+    CU(cudaMemcpyAsync(dl, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    const size_t pool = grow > 1 ? std::min<size_t>(std::max<size_t>(e->pipe_pool_bytes, size_t(64) << 20) * grow, size_t(64) << 30)
+                                 : e->pipe_pool_bytes;
+    size_t i0 = 0;
+    while (i0 < list.size()) {
+        size_t i1 = i0, est = 0, hits = 0;
+        while (i1 < list.size()) {
+            const int c = list[i1];
+            const size_t h = (size_t)(e->h_hit_off[c + 1] - e->h_hit_off[c]), g = (size_t)(e->h_locus_off[c + 1] - e->h_locus_off[c]);
+            const size_t need = 190 * h + 96 * g + 9000;
+            if (i1 > i0 && est + need > pool) break;
+            est += need;
+            hits += h;
+            ++i1;
+        }
+        if ((rc = launch_pipeline(e, ctr, dl + i0, 0, (int64_t)(i1 - i0), hits, 0, grow))) return rc;
+        i0 = i1;
     }
-    int rc = alloc_outputs(e);
-    if (rc) return rc;
-    DevCounters *ctr;
-    if ((rc = outbuf(e, e->ctr, 1, &ctr))) return rc;
-    int64_t *cm_off, *cm_counts, *cm_index, *cm_totals, *scan_tmp;
-    int32_t *cm_na;
-    if ((rc = outbuf(e, e->cm[0], (size_t)e->n + 1, &cm_off))) return rc;
-    if ((rc = outbuf(e, e->cm[1], (size_t)e->n, &cm_na))) return rc;
-    if ((rc = outbuf(e, e->cm[2], 8, &cm_counts))) return rc;
-    if ((rc = outbuf(e, e->cm[3], (size_t)e->n, &cm_index))) return rc;
-    cm_totals = cm_counts + 4;
-    if ((rc = outbuf(e, e->scratch, compaction_scratch_elems(e->n), &scan_tmp))) return rc;
-
-    e->stats = wfl_stats{};
-    e->stats.contigs = e->n;
-    e->stats.hits = e->nh;
-    e->stats.loci = e->nl;
-    DevCounters hc{};
-    DevCounters acc{};
-    int grid = e->sm_count * e->ctas_per_sm;
-    size_t slab_bytes = e->slab_bytes;
-    const int64_t *work_list = nullptr;
-    int64_t n_work = e->n;
-    std::vector<int64_t> replay;
-    bool restart = false;
-    CU(cudaEventRecord(e->ev[1], e->stream));
-    for (int attempt = 0;; ++attempt) {
-        char *slab;
-        if ((rc = outbuf(e, e->slab, (size_t)grid * slab_bytes, &slab))) return rc;
-        if (attempt == 0 || restart) {
-            CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
-            restart = false;
-        } else {
-            // replay: keep the member-pool bump pointer and the statistics, reset the work queue
-            hc.next_work = 0;
-            hc.n_overflow = 0;
-            hc.slab_need_max = 0;
-            CU(cudaMemcpyAsync(ctr, &hc, sizeof hc, cudaMemcpyHostToDevice, e->stream));
-        }
-        ScoreArgs a{};
-        a.b = e->b;
-        a.t = e->tax;
-        a.o = e->o;
-        a.P = e->P;
-        a.ctr = ctr;
-        a.work_list = work_list;
-        a.n_work = n_work;
-        a.slab = slab;
-        a.slab_bytes = slab_bytes;
-        a.smem_bytes = e->smem_bytes;
-        a.plan_nmax = e->plan_nmax;
-        a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
-        a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
-        a.plan_tree = e->use_tree ? static_cast<const TreeEntry *>(e->plan_tree.p) : nullptr;
-        a.dbg_contig = -1;
-        if (attempt == 0 && e->n > 0 && (src != nullptr || e->mode == 2)) {
-            // The batch is cut into chunks of contigs.  Plugin call (src != nullptr): chunk k+1 crosses
-            // PCIe on the copy stream while chunk k is scored on the compute stream.  Pipeline mode: a
-            // chunk is also the sub-batch whose intermediate state shares the workspace pool.
-            if (e->chunks.size() < 2 || e->chunks.back() != e->n)
-                plan_chunks(e, e->h_hit_off.data(), e->h_locus_off.data(), false);
-            bool used_slot1 = false;
-            for (size_t k = 0; k + 1 < e->chunks.size(); ++k) {
-                const int64_t c0 = e->chunks[k], c1 = e->chunks[k + 1];
-                // plugin call: sub-batches alternate between two compute streams, so the tail of one
-                // sub-batch's kernel chain (11+ dependent launches, each ending on its slowest contig)
-                // is filled by the next sub-batch's kernels instead of idling the SMs
-                const bool streamed = src != nullptr && e->chunks_streamed;
-                const int slot = (e->mode == 2 && e->n_slots > 1 && e->chunks.size() > 2) ? (int)(k & 1) : 0;
-                if (slot && !used_slot1) {
-                    CU(cudaEventRecord(e->ev_join, e->stream));   // orders stream2 after the counter reset above
-                    CU(cudaStreamWaitEvent(e->stream2, e->ev_join, 0));
-                    used_slot1 = true;
-                }
-                if (streamed) CU(cudaStreamWaitEvent(slot ? e->stream2 : e->stream, e->chunk_ev[k], 0));
-                if (e->mode == 2) {
-                    if ((rc = launch_pipeline_chunk(e, a, c0, c1, slot))) return rc;
-                } else {
-                    CU(cudaMemsetAsync(&ctr->next_work, 0, sizeof(unsigned long long), e->stream));
-                    a.work_base = c0;
-                    a.n_work = c1 - c0;
-                    if (e->mode == 1)
-                        launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, a.n_work), e->stream);
-                    else
-                        launch_score_kernel(a, (int)std::min<int64_t>(grid, a.n_work), e->threads, e->stream);
-                    CU(cudaGetLastError());
-                    e->stats.kernel_launches++;
-                }
-            }
-            if (used_slot1) {
-                CU(cudaEventRecord(e->ev_join, e->stream2));
-                CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
-            }
-        } else if (n_work > 0) {
-            if (e->mode != 0)
-                launch_score_kernel_warp(a, (int)std::min<int64_t>(grid, n_work), e->stream);
-            else
-                launch_score_kernel(a, (int)std::min<int64_t>(grid, n_work), e->threads, e->stream);
-            CU(cudaGetLastError());
-            e->stats.kernel_launches++;
-        }
-        if (attempt == 0) CU(cudaEventRecord(e->ev[2], e->stream));
-        trace("kernels launched");
-        CU(cudaMemcpyAsync(&hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        trace("kernels finished");
-        acc = hc;
-        if (hc.n_badinput) {
-            set_err(e, "%llu contig(s) carry a hit taxon index outside the taxonomy", hc.n_badinput);
-            return WFL_ERR_ARG;
-        }
-        if (hc.n_runaway) {
-            set_err(e, "Runaway taxonomic recursion in %llu contig(s)", hc.n_runaway);
-            return WFL_ERR_RUNAWAY;
-        }
-        if ((int64_t)hc.mem_pool_used > e->o.mem_pool_cap) {
-            // melded-member staging pool too small: grow it and redo the whole batch
-            if (attempt > 8) { set_err(e, "member pool keeps overflowing"); return WFL_ERR_CUDA; }
-            Buf nb;
-            if ((rc = ensure(e, nb, (size_t)hc.mem_pool_used * sizeof(int32_t) * 2))) return rc;
-            cudaFree(e->out[16].p);
-            e->out[16] = nb;
-            e->o.mem_pool = static_cast<int32_t *>(nb.p);
-            e->o.mem_pool_cap = (int64_t)(nb.cap / sizeof(int32_t));
-            work_list = nullptr;
-            n_work = e->n;
-            restart = true;
-            e->stats.workspace_retries++;
-            continue;
-        }
-        if (hc.n_overflow == 0) break;
-        if (attempt > 8) { set_err(e, "workspace keeps overflowing (need %llu bytes)", hc.slab_need_max); return WFL_ERR_CUDA; }
-        // replay the contigs that outgrew their workspace with a slab of the size they asked for
-        std::vector<uint8_t> st((size_t)e->n);
-        CU(cudaMemcpy(st.data(), e->o.status, (size_t)e->n, cudaMemcpyDeviceToHost));
-        replay.clear();
-        for (int64_t c = 0; c < e->n; ++c)
-            if (st[c] == 1) replay.push_back(c);
-        e->stats.workspace_retries += (int64_t)replay.size();
-        slab_bytes = std::max<size_t>((size_t)hc.slab_need_max, 2 * slab_bytes);
-        slab_bytes = (slab_bytes + 255) & ~size_t(255);
-        size_t budget = size_t(8) << 30;
-        grid = (int)std::max<size_t>(1, std::min<size_t>({(size_t)grid, replay.size(), budget / slab_bytes}));
-        int64_t *wl;
-        if ((rc = outbuf(e, e->work, replay.size(), &wl))) return rc;
-        CU(cudaMemcpyAsync(wl, replay.data(), replay.size() * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
-        work_list = wl;
-        n_work = (int64_t)replay.size();
-    }
-    CompactArgs ca{};
-    ca.n = e->n;
-    ca.o = e->o;
-    ca.member_off = cm_off;
-    ca.n_members_a = cm_na;
-    ca.call_counts = cm_counts;
-    ca.call_index = cm_index;
-    ca.scan_tmp = scan_tmp;
-    ca.totals = cm_totals;
-    // members: compact into a buffer as large as the staging pool
-    int32_t *cm_members;
-    if ((rc = outbuf(e, e->cm[4], (size_t)e->o.mem_pool_cap, &cm_members))) return rc;
-    ca.members = cm_members;
-    ca.members_cap = e->o.mem_pool_cap;
-    e->stats.kernel_launches += launch_compaction(ca, e->stream);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(e->ev[3], e->stream));
-    int64_t totals[4];
-    CU(cudaMemcpyAsync(totals, cm_totals, sizeof totals, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    e->members_total = totals[0];
-    e->stats.matched_pairs = (int64_t)acc.matched_pairs;
-    e->stats.groups = (int64_t)acc.groups;
-    e->stats.levels = (int64_t)acc.levels;
-    e->stats.pairs_tested = (int64_t)acc.pairs_tested;
-    e->stats.pairs_scored = (int64_t)acc.pairs_scored;
-    e->stats.smem_contigs = (int64_t)acc.smem_contigs;
-    for (int q = 0; q < 12; ++q) e->stats.phase_cycles[q] = (int64_t)acc.phase_cycles[q];
-    CU(cudaEventElapsedTime(&e->stats.ms_score_kernel, e->ev[1], e->ev[2]));
-    CU(cudaEventElapsedTime(&e->stats.ms_kernels, e->ev[1], e->ev[3]));
-    e->have_results = true;
     return WFL_OK;
 }
 
-int stage_inputs(wfl_engine *e, const wfl_batch *in, bool copy_all) {
-    if (!e->have_params || !e->have_tax) {
-        set_err(e, "set params and taxonomy before uploading a batch");
-        return WFL_ERR_STATE;
+// Capacities of the fast kernel's shared-memory slice, chosen from the shape of the batch (options override).
+void choose_fast_cfg(wfl_engine *e) {
+    const double hbar = e->n > 0 ? (double)e->nh / (double)e->n : 0.0;        // hits per contig
+    const double kbar = e->nl > 0 ? (double)e->nh / (double)e->nl : 0.0;      // hits per locus
+    auto r32 = [](double x) { return (int)((x + 31.0) / 32.0) * 32; };
+    int K = e->fast_kcap ? e->fast_kcap : std::min(1024, std::max(64, r32(1.8 * kbar + 24)));
+    int T = e->fast_tcap ? e->fast_tcap : std::min(2048, std::max(64, r32(0.6 * hbar + 40)));
+    int N = e->fast_ncap ? e->fast_ncap : std::min(8192, std::max(96, r32(0.9 * hbar + 48)));
+    K = (K + 1) & ~1;
+    int C = 64;
+    while (C * 3 < T * 4) C <<= 1;   // load factor <= 0.75
+    for (;;) {
+        fast_layout(e->fcfg, K, C, T, N, e->S > 0);
+        if ((size_t)fast_warps_per_cta() * e->fcfg.slice_bytes + 1024 <= e->smem_optin) break;
+        // does not fit one CTA: shrink the largest consumers
+        if (N > 96) N = std::max(96, N / 2);
+        else if (T > 64) { T = std::max(64, T / 2); C = std::max(64, C / 2); }
+        else if (K > 64) K = std::max(64, K / 2);
+        else break;
     }
-    int rc = check_batch(e, in);
-    if (rc) return rc;
-    e->have_batch = e->have_results = false;
-    e->n = in->n_contigs;
-    e->nh = in->n_hits;
-    e->nl = in->n_loci;
-    e->S = e->P.p.n_systems;
-    DevBatch &b = e->b;
-    b.n_contigs = e->n;
-    b.n_hits = e->nh;
-    b.n_loci = e->nl;
-    const size_t n1 = (size_t)e->n + 1, nh = (size_t)e->nh, nl = (size_t)e->nl;
-    e->chunks.clear();
-    e->chunks_streamed = false;
-    // The CSR offsets go first.  Plugin call: on the COPY stream, ahead of chunk 0 (two streams feeding the
-    // same DMA queue are not ordered by issue time: on the compute stream they ended up behind the whole
-    // bulk transfer and the first kernel with them); chunk 0's event covers them.
-    cudaStream_t os = copy_all ? e->stream : e->copy_stream;
-    CU(cudaEventRecord(e->ev[0], os));
-    if ((rc = upload(e, e->in[0], in->hit_off, n1, &b.hit_off, os))) return rc;
-    if ((rc = upload(e, e->in[1], in->locus_off, n1, &b.locus_off, os))) return rc;
-    if (!copy_all) {
-        // plugin call: device arrays only, and the chunked H2D copies start NOW on the copy stream -- the
-        // host-side preparation below (plan table, offsets) and the kernels overlap with the transfer
-        rc = 0;
-        rc |= outbuf(e, e->in[2], nh, const_cast<int32_t **>(&b.hit_qstart));
-        rc |= outbuf(e, e->in[3], nh, const_cast<int32_t **>(&b.hit_qend));
-        rc |= outbuf(e, e->in[4], nh, const_cast<int32_t **>(&b.hit_taxon));
-        rc |= outbuf(e, e->in[5], nh, const_cast<double **>(&b.hit_score));
-        rc |= outbuf(e, e->in[6], nh, const_cast<double **>(&b.hit_scov));
-        rc |= outbuf(e, e->in[7], nh, const_cast<int8_t **>(&b.hit_strand));
-        b.hit_sysmask = nullptr;
-        if (e->S > 0) rc |= outbuf(e, e->in[8], nh, const_cast<uint32_t **>(&b.hit_sysmask));
-        rc |= outbuf(e, e->in[9], nl, const_cast<int32_t **>(&b.locus_start));
-        rc |= outbuf(e, e->in[10], nl, const_cast<int32_t **>(&b.locus_end));
-        rc |= outbuf(e, e->in[11], nl, const_cast<int8_t **>(&b.locus_strand));
-        if (rc) return WFL_ERR_CUDA;
-        if (e->n > 0) {
-            plan_chunks(e, in->hit_off, in->locus_off, true);
-            trace("chunks planned");
-            if ((rc = issue_chunk_copies(e, in))) return rc;
-            trace("chunk copies issued");
-        }
-    }
-    {
-        int maxlen = 0;
-        for (int64_t i = 0; i < in->n_loci; ++i) {
-            int d = in->locus_end[i] - in->locus_start[i];
-            d = (d < 0 ? -d : d) + 1;
-            maxlen = d > maxlen ? d : maxlen;
-        }
-        if ((rc = ensure_plan_table(e, maxlen))) return rc;
-    }
-    e->h_hit_off.assign(in->hit_off, in->hit_off + n1);
-    e->h_locus_off.assign(in->locus_off, in->locus_off + n1);
-    if (copy_all) {
-        if ((rc = upload(e, e->in[2], in->hit_qstart, nh, &b.hit_qstart))) return rc;
-        if ((rc = upload(e, e->in[3], in->hit_qend, nh, &b.hit_qend))) return rc;
-        if ((rc = upload(e, e->in[4], in->hit_taxon, nh, &b.hit_taxon))) return rc;
-        if ((rc = upload(e, e->in[5], in->hit_score, nh, &b.hit_score))) return rc;
-        if ((rc = upload(e, e->in[6], in->hit_scov, nh, &b.hit_scov))) return rc;
-        if ((rc = upload(e, e->in[7], in->hit_strand, nh, &b.hit_strand))) return rc;
-        b.hit_sysmask = nullptr;
-        if (e->S > 0 && (rc = upload(e, e->in[8], in->hit_sysmask, nh, &b.hit_sysmask))) return rc;
-        if ((rc = upload(e, e->in[9], in->locus_start, nl, &b.locus_start))) return rc;
-        if ((rc = upload(e, e->in[10], in->locus_end, nl, &b.locus_end))) return rc;
-        if ((rc = upload(e, e->in[11], in->locus_strand, nl, &b.locus_strand))) return rc;
-    }
-    trace("host prep done");
-    if (copy_all) {
-        CU(cudaEventRecord(e->ev[1], e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        CU(cudaEventElapsedTime(&e->stats.ms_h2d, e->ev[0], e->ev[1]));
-    } else if (e->n == 0) {
-        CU(cudaStreamSynchronize(e->copy_stream));   // no chunk event will order the (empty) offsets
-    }
-    e->have_batch = true;
+    const int cpsm = std::max(1, fast_ctas_per_sm(e->fcfg, e->packed, 0));
+    e->fast_grid = e->sm_count * cpsm;
+}
+
+int launch_fast_range(wfl_engine *e, DevCounters *ctr, int64_t c0, int64_t n_work, int launch_idx, cudaStream_t stream) {
+    FastArgs a{};
+    a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
+    a.cfg = e->fcfg;
+    a.wq = static_cast<unsigned long long *>(e->fast_wq.p) + launch_idx;
+    a.n_work = n_work; a.work_base = c0; a.work_list = nullptr;
+    a.fb_list = static_cast<int *>(e->fb_list.p);
+    a.anc = static_cast<const int *>(e->anc.p);
+    a.anc_rows = e->anc_rows;
+    a.guard = 1e-12;
+    a.plan_nmax = e->plan_nmax;
+    a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
+    a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
+    a.scratch = static_cast<char *>(e->fast_scratch.p);
+    const int wpc = fast_warps_per_cta();
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(e->fast_grid, (n_work + wpc - 1) / wpc));
+    cudaError_t err = launch_fast(a, e->packed, grid, stream);
+    if (err != cudaSuccess) { set_err(e, "fast kernel launch failed: %s", cudaGetErrorString(err)); return WFL_ERR_CUDA; }
+    e->stats.kernel_launches++;
     return WFL_OK;
 }
 
@@ -743,22 +561,11 @@ int d2h(wfl_engine *e, T *dst, const T *src, size_t n) {
     return WFL_OK;
 }
 
-int download(wfl_engine *e, wfl_results *out) {
-    if (!e->have_results) {
-        set_err(e, "no results to download");
-        return WFL_ERR_STATE;
-    }
-    if (!out) { set_err(e, "null results"); return WFL_ERR_ARG; }
-    out->members_used = e->members_total;
-    if (out->members && out->members_capacity < e->members_total) {
-        set_err(e, "members buffer too small: need %lld", (long long)e->members_total);
-        return WFL_ERR_CAPACITY;
-    }
+// Queue the D2H copies of every result array; `members` copies that many member entries.
+int queue_downloads(wfl_engine *e, wfl_results *out, size_t members) {
     const size_t n = (size_t)e->n, nl = (size_t)e->nl, S = (size_t)e->S;
     const DevOut &o = e->o;
     int rc = 0;
-    float h2d = e->stats.ms_h2d;
-    CU(cudaEventRecord(e->ev[4], e->stream));
     rc |= d2h(e, out->call, o.call, n);
     rc |= d2h(e, out->direction, o.direction, n);
     rc |= d2h(e, out->lifts, o.lifts, n);
@@ -774,15 +581,350 @@ int download(wfl_engine *e, wfl_results *out) {
     rc |= d2h(e, out->ann_winner, o.ann_winner, nl * S);
     rc |= d2h(e, out->member_off, static_cast<const int64_t *>(e->cm[0].p), n + 1);
     rc |= d2h(e, out->n_members_a, static_cast<const int32_t *>(e->cm[1].p), n);
-    rc |= d2h(e, out->members, static_cast<const int32_t *>(e->cm[4].p), (size_t)e->members_total);
+    rc |= d2h(e, out->members, static_cast<const int32_t *>(e->cm[4].p), members);
     rc |= d2h(e, out->call_counts, static_cast<const int64_t *>(e->cm[2].p), 3);
     rc |= d2h(e, out->call_index, static_cast<const int64_t *>(e->cm[3].p), n);
-    if (rc) return WFL_ERR_CUDA;
+    return rc ? WFL_ERR_CUDA : WFL_OK;
+}
+
+int sync_stream(wfl_engine *e) {
+    CU(cudaStreamSynchronize(e->stream));
+    e->stats.host_syncs++;
+    return WFL_OK;
+}
+
+// Score the resident (or in-flight: `streamed`) batch.  Common case = ONE host synchronisation: the fast kernels, the
+// compaction and -- with `out` -- the result copies are queued back to back, the counters ride the same stream, and only
+// if the fast path handed contigs back (or a workspace overflowed) does the host queue the exact pipeline and a second
+// round of compaction + copies.
+int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
+    *restart = false;
+    int rc = alloc_outputs(e);
+    if (rc) return rc;
+    DevCounters *ctr;
+    if ((rc = outbuf(e, e->ctr, 1, &ctr))) return rc;
+    int64_t *cm_off, *cm_counts, *cm_index, *cm_totals, *scan_tmp;
+    int32_t *cm_na, *cm_members;
+    if ((rc = outbuf(e, e->cm[0], (size_t)e->n + 1, &cm_off))) return rc;
+    if ((rc = outbuf(e, e->cm[1], (size_t)e->n, &cm_na))) return rc;
+    if ((rc = outbuf(e, e->cm[2], 8, &cm_counts))) return rc;
+    if ((rc = outbuf(e, e->cm[3], (size_t)e->n, &cm_index))) return rc;
+    if ((rc = outbuf(e, e->cm[4], (size_t)e->o.mem_pool_cap, &cm_members))) return rc;
+    cm_totals = cm_counts + 4;
+    if ((rc = outbuf(e, e->scratch, compaction_scratch_elems(e->n), &scan_tmp))) return rc;
+    const bool use_fast = !e->exact && e->P.p.min_overlap > 0.0;
+    int *fb_list = nullptr;
+    unsigned long long *fwq = nullptr;
+    if (use_fast) {
+        choose_fast_cfg(e);
+        char *fs;
+        if ((rc = outbuf(e, e->fb_list, (size_t)e->n + 1, &fb_list))) return rc;
+        if ((rc = outbuf(e, e->fast_wq, 256, &fwq))) return rc;
+        if ((rc = outbuf(e, e->fast_scratch, (size_t)e->fast_grid * fast_warps_per_cta() * e->fcfg.Kcap * 16, &fs))) return rc;
+        CU(cudaMemsetAsync(fwq, 0, 256 * sizeof(unsigned long long), e->stream));
+    }
+    CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
+    CU(cudaEventRecord(e->ev[1], e->stream));
+
+    if (e->n > 0) {
+        if (e->chunks.size() < 2 || e->chunks.back() != e->n)
+            plan_chunks(e, e->h_hit_off.data(), e->h_locus_off.data(), false, 29);
+        bool used_slot1 = false;
+        for (size_t k = 0; k + 1 < e->chunks.size(); ++k) {
+            const int64_t c0 = e->chunks[k], c1 = e->chunks[k + 1];
+            // sub-batches alternate between two compute streams, so that the tail of one sub-batch's kernels (each ends
+            // on its slowest contig) is filled by the next sub-batch's kernels instead of idling the SMs
+            const int slot = (e->n_slots > 1 && e->chunks.size() > 2) ? (int)(k & 1) : 0;
+            if (slot && !used_slot1) {
+                CU(cudaEventRecord(e->ev_join, e->stream));   // orders stream2 after the resets above
+                CU(cudaStreamWaitEvent(e->stream2, e->ev_join, 0));
+                used_slot1 = true;
+            }
+            cudaStream_t st = slot ? e->stream2 : e->stream;
+            if (streamed && e->chunks_streamed) CU(cudaStreamWaitEvent(st, e->chunk_ev[k], 0));
+            if (use_fast) {
+                if (k >= 250) { set_err(e, "too many chunks"); return WFL_ERR_ARG; }
+                if ((rc = launch_fast_range(e, ctr, c0, c1 - c0, (int)k, st))) return rc;
+            } else {
+                if ((rc = launch_pipeline(e, ctr, nullptr, c0, c1 - c0, (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]), slot, 1))) return rc;
+            }
+        }
+        if (used_slot1) {
+            CU(cudaEventRecord(e->ev_join, e->stream2));
+            CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+        }
+    }
+    CU(cudaEventRecord(e->ev[2], e->stream));
+    trace("kernels launched");
+
+    CompactArgs ca{};
+    ca.n = e->n;
+    ca.o = e->o;
+    ca.member_off = cm_off;
+    ca.n_members_a = cm_na;
+    ca.call_counts = cm_counts;
+    ca.call_index = cm_index;
+    ca.scan_tmp = scan_tmp;
+    ca.totals = cm_totals;
+    ca.members = cm_members;
+    ca.members_cap = e->o.mem_pool_cap;
+
+    DevCounters hc{};
+    int64_t totals[4] = {0, 0, 0, 0};
+    size_t grow = 1;
+    for (int attempt = 0;; ++attempt) {
+        // (speculative on attempt 0) compaction + counters + result copies, then the one synchronisation
+        e->stats.kernel_launches += launch_compaction(ca, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e->ev[3], e->stream));
+        CU(cudaMemcpyAsync(&hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(totals, cm_totals, sizeof totals, cudaMemcpyDeviceToHost, e->stream));
+        size_t spec_members = 0;
+        if (out) {
+            CU(cudaEventRecord(e->ev[4], e->stream));
+            spec_members = out->members ? (size_t)std::min<int64_t>(out->members_capacity, e->o.mem_pool_cap) : 0;
+            if ((rc = queue_downloads(e, out, spec_members))) return rc;
+            CU(cudaEventRecord(e->ev[6], e->stream));
+        }
+        if ((rc = sync_stream(e))) return rc;
+        trace("synchronised");
+        if (hc.n_badinput) {
+            set_err(e, "%llu contig(s) carry a hit taxon index outside the taxonomy", hc.n_badinput);
+            return WFL_ERR_ARG;
+        }
+        if (hc.n_runaway) {
+            set_err(e, "Runaway taxonomic recursion in %llu contig(s)", hc.n_runaway);
+            return WFL_ERR_RUNAWAY;
+        }
+        if ((int64_t)hc.mem_pool_used > e->o.mem_pool_cap) {
+            // melded-member staging pool too small: grow it and redo the whole batch
+            Buf nb;
+            if ((rc = ensure(e, nb, (size_t)hc.mem_pool_used * sizeof(int32_t) * 2))) return rc;
+            cudaFree(e->out[16].p);
+            e->out[16] = nb;
+            e->stats.workspace_retries++;
+            *restart = true;
+            return WFL_OK;
+        }
+        // contigs for the exact pipeline: fast-path fallbacks (first round) and workspace overflows (status 1)
+        std::vector<int> list;
+        if (attempt == 0 && hc.n_fallback) {
+            list.resize((size_t)hc.n_fallback);
+            CU(cudaMemcpy(list.data(), fb_list, list.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            std::sort(list.begin(), list.end());
+            e->stats.fallback_contigs = (int64_t)list.size();
+        } else if (hc.n_overflow) {
+            std::vector<uint8_t> st((size_t)e->n);
+            CU(cudaMemcpy(st.data(), e->o.status, (size_t)e->n, cudaMemcpyDeviceToHost));
+            for (int64_t c = 0; c < e->n; ++c)
+                if (st[c] == 1) list.push_back((int)c);
+            e->stats.workspace_retries += (int64_t)list.size();
+            grow *= 4;
+        }
+        if (list.empty()) break;
+        if (attempt > 8) { set_err(e, "workspace keeps overflowing"); return WFL_ERR_CUDA; }
+        unsigned long long zero = 0;
+        CU(cudaMemcpyAsync(&ctr->n_overflow, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(&ctr->n_fallback, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
+        if ((rc = run_pipeline_list(e, ctr, list, grow))) return rc;
+    }
+    e->members_total = totals[0];
+    if (out) {
+        out->members_used = e->members_total;
+        if (out->members && out->members_capacity < e->members_total) {
+            set_err(e, "members buffer too small: need %lld", (long long)e->members_total);
+            e->have_results = true;
+            return WFL_ERR_CAPACITY;
+        }
+        CU(cudaEventElapsedTime(&e->stats.ms_d2h, e->ev[4], e->ev[6]));
+    }
+    e->stats.matched_pairs = (int64_t)hc.matched_pairs;
+    e->stats.groups = (int64_t)hc.groups;
+    e->stats.levels = (int64_t)hc.levels;
+    e->stats.pairs_tested = (int64_t)hc.pairs_tested;
+    e->stats.pairs_scored = (int64_t)hc.pairs_scored;
+    e->stats.smem_contigs = (int64_t)hc.smem_contigs;
+    e->stats.guard_trips = (int64_t)hc.guard_trips;
+    e->stats.refined_groups = (int64_t)hc.refined_groups;
+    for (int q = 0; q < 12; ++q) e->stats.phase_cycles[q] = (int64_t)hc.phase_cycles[q];
+    CU(cudaEventElapsedTime(&e->stats.ms_score_kernel, e->ev[1], e->ev[2]));
+    CU(cudaEventElapsedTime(&e->stats.ms_kernels, e->ev[1], e->ev[3]));
+    e->have_results = true;
+    return WFL_OK;
+}
+
+int run_kernels(wfl_engine *e, bool streamed, wfl_results *out) {
+    if (!e->have_params || !e->have_tax || !e->have_batch) {
+        set_err(e, "params, taxonomy and batch must be set before running");
+        return WFL_ERR_STATE;
+    }
+    const float h2d = e->stats.ms_h2d;
+    e->stats = wfl_stats{};
+    e->stats.ms_h2d = h2d;
+    e->stats.contigs = e->n;
+    e->stats.hits = e->nh;
+    e->stats.loci = e->nl;
+    for (int round = 0; round < 8; ++round) {
+        bool restart = false;
+        int rc = run_once(e, streamed, out, &restart);
+        if (rc || !restart) return rc;
+    }
+    set_err(e, "member pool keeps overflowing");
+    return WFL_ERR_CUDA;
+}
+
+int stage_inputs(wfl_engine *e, const HostBatch &in, bool copy_all) {
+    if (!e->have_params || !e->have_tax) {
+        set_err(e, "set params and taxonomy before uploading a batch");
+        return WFL_ERR_STATE;
+    }
+    int rc = check_host_batch(e, in);
+    if (rc) return rc;
+    e->have_batch = e->have_results = false;
+    e->n = in.n;
+    e->nh = in.nh;
+    e->nl = in.nl;
+    e->S = e->P.p.n_systems;
+    e->packed = in.packed;
+    DevBatch &b = e->b;
+    b.n_contigs = e->n;
+    b.n_hits = e->nh;
+    b.n_loci = e->nl;
+    const size_t n1 = (size_t)e->n + 1, nh = (size_t)e->nh, nl = (size_t)e->nl;
+    e->chunks.clear();
+    e->chunks_streamed = false;
+    // every fallible allocation first: no H2D copy may be in flight when this function fails (the caller owns the
+    // host buffers)
+    for (int i = 0; i < in.ncol; ++i)
+        if (in.col[i]) {
+            void *p;
+            if ((rc = outbuf(e, e->in[2 + i], nh * in.esz[i], reinterpret_cast<char **>(&p)))) return rc;
+        }
+    {
+        int32_t *p4;
+        int8_t *p1;
+        int64_t *p8;
+        if ((rc = outbuf(e, e->in[9], nl, &p4)) || (rc = outbuf(e, e->in[10], nl, &p4)) || (rc = outbuf(e, e->in[11], nl, &p1)) ||
+            (rc = outbuf(e, e->in[0], n1, &p8)) || (rc = outbuf(e, e->in[1], n1, &p8)))
+            return rc;
+    }
+    {
+        int maxlen = 0;
+        for (int64_t i = 0; i < in.nl; ++i) {
+            int d = in.locus_end[i] - in.locus_start[i];
+            d = (d < 0 ? -d : d) + 1;
+            maxlen = d > maxlen ? d : maxlen;
+        }
+        if ((rc = ensure_plan_table(e, maxlen))) return rc;
+    }
+    bind_device_batch(e);
+    b.hit_off = static_cast<const int64_t *>(e->in[0].p);
+    b.locus_off = static_cast<const int64_t *>(e->in[1].p);
+    // The CSR offsets go first.  Plugin call: on the COPY stream, ahead of chunk 0 (two streams feeding the same DMA
+    // queue are not ordered by issue time: on the compute stream they ended up behind the whole bulk transfer and the
+    // first kernel with them); chunk 0's event covers them.
+    cudaStream_t os = copy_all ? e->stream : e->copy_stream;
+    CU(cudaEventRecord(e->ev[0], os));
+    CU(cudaMemcpyAsync(e->in[0].p, in.hit_off, n1 * 8, cudaMemcpyHostToDevice, os));
+    CU(cudaMemcpyAsync(e->in[1].p, in.locus_off, n1 * 8, cudaMemcpyHostToDevice, os));
+    const size_t row = hit_row_bytes(in);
+    if (!copy_all) {
+        // plugin call: the chunked H2D copies start NOW on the copy stream; the host-side preparation below and the
+        // kernels overlap with the transfer
+        if (e->n > 0) {
+            plan_chunks(e, in.hit_off, in.locus_off, true, row);
+            trace("chunks planned");
+            if ((rc = issue_chunk_copies(e, in))) { cudaStreamSynchronize(e->copy_stream); return rc; }
+            trace("chunk copies issued");
+        }
+    } else {
+        for (int i = 0; i < in.ncol; ++i)
+            if (in.col[i] && nh) CU(cudaMemcpyAsync(dev_col(e, i), in.col[i], nh * in.esz[i], cudaMemcpyHostToDevice, os));
+        if (nl) {
+            CU(cudaMemcpyAsync(e->in[9].p, in.locus_start, nl * 4, cudaMemcpyHostToDevice, os));
+            CU(cudaMemcpyAsync(e->in[10].p, in.locus_end, nl * 4, cudaMemcpyHostToDevice, os));
+            CU(cudaMemcpyAsync(e->in[11].p, in.locus_strand, nl, cudaMemcpyHostToDevice, os));
+        }
+    }
+    e->h_hit_off.assign(in.hit_off, in.hit_off + n1);
+    e->h_locus_off.assign(in.locus_off, in.locus_off + n1);
+    trace("host prep done");
+    if (copy_all) {
+        CU(cudaEventRecord(e->ev[1], e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaEventElapsedTime(&e->stats.ms_h2d, e->ev[0], e->ev[1]));
+    } else if (e->n == 0) {
+        CU(cudaStreamSynchronize(e->copy_stream));   // no chunk event will order the (empty) offsets
+    }
+    e->have_batch = true;
+    return WFL_OK;
+}
+
+int download(wfl_engine *e, wfl_results *out) {
+    if (!e->have_results) {
+        set_err(e, "no results to download");
+        return WFL_ERR_STATE;
+    }
+    if (!out) { set_err(e, "null results"); return WFL_ERR_ARG; }
+    out->members_used = e->members_total;
+    if (out->members && out->members_capacity < e->members_total) {
+        set_err(e, "members buffer too small: need %lld", (long long)e->members_total);
+        return WFL_ERR_CAPACITY;
+    }
+    int rc;
+    CU(cudaEventRecord(e->ev[4], e->stream));
+    if ((rc = queue_downloads(e, out, (size_t)e->members_total))) return rc;
     CU(cudaEventRecord(e->ev[6], e->stream));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaEventElapsedTime(&e->stats.ms_d2h, e->ev[4], e->ev[6]));
-    e->stats.ms_h2d = h2d;
     return WFL_OK;
+}
+
+int score_host_batch(wfl_engine *e, const HostBatch &hb, wfl_results *out) {
+    trace("begin");
+    int rc = stage_inputs(e, hb, false);
+    if (rc) return rc;
+    trace("inputs staged, copies in flight");
+    rc = run_kernels(e, true, out);
+    if (rc && rc != WFL_ERR_CAPACITY) {
+        // the caller owns the host buffers: nothing of ours may still be reading them when we return an error
+        cudaStreamSynchronize(e->copy_stream);
+        cudaStreamSynchronize(e->stream);
+        cudaStreamSynchronize(e->stream2);
+        return rc;
+    }
+    trace("kernels + compaction + downloads done");
+    float h2d = 0.f;
+    if (e->n > 0 && cudaEventElapsedTime(&h2d, e->ev[0], e->ev[5]) == cudaSuccess) e->stats.ms_h2d = h2d;
+    return rc;
+}
+
+// ---- results packed into one device buffer (multi-GPU gather) ----
+struct PackArgs {
+    const void *src[18];
+    int64_t off[18], bytes[18];
+    char *dst;
+    int64_t header[8];
+};
+
+__global__ void wfl_pack_results_kernel(const PackArgs a) {
+    const int sec = blockIdx.y;
+    const int64_t n16 = (a.bytes[sec] + 15) / 16;
+    const uint4 *s = static_cast<const uint4 *>(a.src[sec]);
+    uint4 *d = reinterpret_cast<uint4 *>(a.dst + a.off[sec]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+    if (sec == 0 && blockIdx.x == 0 && threadIdx.x < 8) reinterpret_cast<int64_t *>(a.dst)[threadIdx.x] = a.header[threadIdx.x];
+}
+
+int64_t results_layout(int64_t n, int64_t nl, int32_t S, int64_t members, int64_t off[18]) {
+    const int64_t sz[18] = {n, n, 4 * n, 4 * n, 4 * n, 4 * n, 4 * n, 4 * n, 8 * n, 8 * n, 8 * (n + 1), 4 * n, 4 * members,
+                            nl, nl, 4 * nl * S, 8 * 3, 8 * n};
+    int64_t o = 64;
+    for (int i = 0; i < 18; ++i) {
+        off[i] = o;
+        o += (sz[i] + 15) & ~int64_t(15);
+    }
+    return o;
 }
 
 }  // namespace
@@ -799,6 +941,22 @@ int wfl_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+int wfl_set_option(wfl_engine *e, const char *name, int64_t value) {
+    if (!e || !name) return WFL_ERR_ARG;
+    const std::string k(name);
+    if (k == "exact") e->exact = value != 0;
+    else if (k == "fast_kcap") e->fast_kcap = (int)std::max<int64_t>(0, value);
+    else if (k == "fast_tcap") e->fast_tcap = (int)std::max<int64_t>(0, value);
+    else if (k == "fast_ncap") e->fast_ncap = (int)std::max<int64_t>(0, value);
+    else if (k == "pool_mb") e->pipe_pool_bytes = (size_t)std::max<int64_t>(0, value) << 20;
+    else if (k == "chunk_mb") { e->chunk_bytes = (size_t)std::max<int64_t>(1, value) << 20; e->chunk_fixed = true; }
+    else if (k == "streams") e->n_slots = value >= 2 ? 2 : 1;
+    else if (k == "k2_cap") e->k2_cap_override = (size_t)std::max<int64_t>(0, value);
+    else { set_err(e, "unknown option %s", name); return WFL_ERR_ARG; }
+    e->have_results = false;
+    return WFL_OK;
 }
 
 int wfl_create(int device, wfl_engine **out) {
@@ -818,19 +976,16 @@ int wfl_create(int device, wfl_engine **out) {
         return WFL_ERR_CUDA;
     }
     e->sm_count = prop.multiProcessorCount;
-    if (const char *k = getenv("WFL_KERNEL")) {
-        std::string m(k);
-        e->mode = m == "v1" ? 0 : m == "v2" ? 1 : 2;
-    }
-    if (e->mode == 0) { e->threads = 128; e->smem_bytes = 36 * 1024; e->ctas_per_sm = 6; }
-    if (const char *k = getenv("WFL_K2")) { e->use_tree = std::string(k) == "tree"; e->k2_global = std::string(k) != "contig"; }
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    // environment twins of wfl_set_option (read once here)
+    if (const char *k = getenv("WFL_K2")) e->exact = std::string(k) == "exact";
     if (const char *k = getenv("WFL_K2_CAP")) e->k2_cap_override = (size_t)std::max<long long>(0, atoll(k));
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
-    if (const char *k = getenv("WFL_CHUNK_MB")) { e->chunk_bytes = (size_t)atoll(k) << 20; e->chunk_fixed = true; }
-    if (const char *k = getenv("WFL_SPLIT")) e->resident_split = std::max(1, atoi(k));
+    if (const char *k = getenv("WFL_CHUNK_MB")) { e->chunk_bytes = (size_t)std::max<long long>(1, atoll(k)) << 20; e->chunk_fixed = true; }
     if (const char *k = getenv("WFL_STREAMS")) e->n_slots = atoi(k) >= 2 ? 2 : 1;
-    if (const char *k = getenv("WFL_CHUNK_SHRINK")) e->chunk_shrink = std::min(1.0, std::max(0.05, atof(k)));
-    e->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char *k = getenv("WFL_FAST_KCAP")) e->fast_kcap = atoi(k);
+    if (const char *k = getenv("WFL_FAST_TCAP")) e->fast_tcap = atoi(k);
+    if (const char *k = getenv("WFL_FAST_NCAP")) e->fast_ncap = atoi(k);
     for (auto &ev : e->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) {
             delete e;
@@ -849,7 +1004,8 @@ void wfl_destroy(wfl_engine *e) {
     for (auto &b : e->out) fr(b);
     for (auto &b : e->cm) fr(b);
     for (auto &b : e->dbg) fr(b);
-    fr(e->slab); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data); fr(e->plan_tree);
+    fr(e->anc); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data);
+    fr(e->fb_list); fr(e->fast_scratch); fr(e->fast_wq); fr(e->blob); fr(e->status_tmp);
     for (int q = 0; q < 2; ++q) { fr(e->pipe_pool[q]); fr(e->pipe_lists[q]); fr(e->pipe_cnt[q]); fr(e->pipe_wq[q]); }
     fr(e->pipe_ctg);
     for (int q = 0; q < 2; ++q) { fr(e->k2_desc[q]); fr(e->k2_order[q]); fr(e->k2_keys[q]); fr(e->k2_meta[q]); }
@@ -903,12 +1059,14 @@ int wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent, cons
         set_err(e, "root must be its own parent at depth 0");
         return WFL_ERR_ARG;
     }
+    int max_depth = 0;
     for (int32_t i = 0; i < n_nodes; ++i) {
         int32_t p = parent[i];
         if (p < 0 || p >= n_nodes || (i != root_idx && depth[i] != depth[p] + 1)) {
             set_err(e, "taxonomy node %d: parent / depth inconsistent", i);
             return WFL_ERR_ARG;
         }
+        max_depth = std::max(max_depth, (int)depth[i]);
     }
     CU(cudaSetDevice(e->device));
     int rc;
@@ -916,9 +1074,21 @@ int wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent, cons
     if ((rc = upload(e, e->tx[1], depth, (size_t)n_nodes, &e->tax.depth))) return rc;
     if ((rc = upload(e, e->tx[2], leaf_count, (size_t)n_nodes, &e->tax.leaf_count))) return rc;
     if ((rc = upload(e, e->tx[3], listed, (size_t)n_nodes, &e->tax.listed))) return rc;
+    // ancestor table of the fast path: row l = l-th ancestor of every node (raise_taxonomy applied l times,
+    // waafle_orgscorer.py:431-445 with utils.py:386-387); row max_depth is all root
+    {
+        const int rows = std::min(max_depth, 63) + 1;
+        std::vector<int32_t> anc((size_t)rows * n_nodes);
+        for (int32_t i = 0; i < n_nodes; ++i) anc[i] = i;
+        for (int l = 1; l < rows; ++l)
+            for (int32_t i = 0; i < n_nodes; ++i) anc[(size_t)l * n_nodes + i] = parent[anc[(size_t)(l - 1) * n_nodes + i]];
+        const int32_t *d;
+        if ((rc = upload(e, e->anc, anc.data(), anc.size(), &d))) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+        e->anc_rows = rows;
+    }
     CU(cudaStreamSynchronize(e->stream));
-    e->tax_max_depth = 0;
-    for (int32_t i = 0; i < n_nodes; ++i) e->tax_max_depth = std::max(e->tax_max_depth, (int)depth[i]);
+    e->tax_max_depth = max_depth;
     e->tax.n_nodes = n_nodes;
     e->tax.root = root_idx;
     e->tax.unknown = unknown_idx;
@@ -928,18 +1098,21 @@ int wfl_set_taxonomy(wfl_engine *e, int32_t n_nodes, const int32_t *parent, cons
 }
 
 int wfl_upload_batch(wfl_engine *e, const wfl_batch *in) {
-    if (!e) return WFL_ERR_ARG;
+    if (!e || !in) return WFL_ERR_ARG;
     CU(cudaSetDevice(e->device));
-    return stage_inputs(e, in, true);
+    return stage_inputs(e, host_batch(in, e->P.p.n_systems), true);
+}
+
+int wfl_upload_packed(wfl_engine *e, const wfl_packed_batch *in) {
+    if (!e || !in) return WFL_ERR_ARG;
+    CU(cudaSetDevice(e->device));
+    return stage_inputs(e, host_batch(in, e->P.p.n_systems), true);
 }
 
 int wfl_run_resident(wfl_engine *e) {
     if (!e) return WFL_ERR_ARG;
     CU(cudaSetDevice(e->device));
-    float h2d = e->stats.ms_h2d;
-    int rc = run_kernels(e);
-    e->stats.ms_h2d = h2d;
-    return rc;
+    return run_kernels(e, false, nullptr);
 }
 
 int wfl_download_results(wfl_engine *e, wfl_results *out) {
@@ -949,19 +1122,47 @@ int wfl_download_results(wfl_engine *e, wfl_results *out) {
 }
 
 int wfl_score_batch(wfl_engine *e, const wfl_batch *in, wfl_results *out) {
-    if (!e) return WFL_ERR_ARG;
+    if (!e || !in) return WFL_ERR_ARG;
     CU(cudaSetDevice(e->device));
-    trace("begin");
-    int rc = stage_inputs(e, in, false);
-    if (rc) return rc;
-    trace("inputs staged, copies in flight");
-    if ((rc = run_kernels(e, in))) return rc;
-    trace("kernels + compaction done");
-    float h2d = 0.f;
-    if (e->n > 0 && cudaEventElapsedTime(&h2d, e->ev[0], e->ev[5]) == cudaSuccess) e->stats.ms_h2d = h2d;
-    rc = download(e, out);
-    trace("results downloaded");
-    return rc;
+    return score_host_batch(e, host_batch(in, e->P.p.n_systems), out);
+}
+
+int wfl_score_packed(wfl_engine *e, const wfl_packed_batch *in, wfl_results *out) {
+    if (!e || !in) return WFL_ERR_ARG;
+    CU(cudaSetDevice(e->device));
+    return score_host_batch(e, host_batch(in, e->P.p.n_systems), out);
+}
+
+int64_t wfl_packed_results_layout(int64_t n_contigs, int64_t n_loci, int32_t n_systems, int64_t n_members, int64_t offsets[18]) {
+    int64_t tmp[18];
+    return results_layout(n_contigs, n_loci, n_systems, n_members, offsets ? offsets : tmp);
+}
+
+int wfl_pack_results(wfl_engine *e, void **dev_ptr, int64_t *bytes, void **stream) {
+    if (!e || !dev_ptr || !bytes) return WFL_ERR_ARG;
+    if (!e->have_results) { set_err(e, "no results to pack"); return WFL_ERR_STATE; }
+    CU(cudaSetDevice(e->device));
+    PackArgs pa{};
+    const int64_t total = results_layout(e->n, e->nl, e->S, e->members_total, pa.off);
+    int rc;
+    char *blob;
+    if ((rc = outbuf(e, e->blob, (size_t)total, &blob))) return rc;
+    const DevOut &o = e->o;
+    const void *src[18] = {o.call, o.direction, o.lifts, o.clade1, o.clade2, o.lca, o.best1, o.best2, o.crit, o.rank,
+                           e->cm[0].p, e->cm[1].p, e->cm[4].p, o.synteny, o.locus_flags, o.ann_winner, e->cm[2].p, e->cm[3].p};
+    const int64_t n = e->n, nl = e->nl;
+    const int64_t sz[18] = {n, n, 4 * n, 4 * n, 4 * n, 4 * n, 4 * n, 4 * n, 8 * n, 8 * n, 8 * (n + 1), 4 * n, 4 * e->members_total,
+                            nl, nl, 4 * nl * e->S, 8 * 3, 8 * n};
+    for (int i = 0; i < 18; ++i) { pa.src[i] = src[i]; pa.bytes[i] = sz[i]; }
+    pa.dst = blob;
+    pa.header[0] = n; pa.header[1] = nl; pa.header[2] = e->S; pa.header[3] = e->members_total;
+    wfl_pack_results_kernel<<<dim3(64, 18), 256, 0, e->stream>>>(pa);
+    CU(cudaGetLastError());
+    e->stats.kernel_launches++;
+    *dev_ptr = blob;
+    *bytes = total;
+    if (stream) *stream = e->stream;
+    return WFL_OK;
 }
 
 int wfl_host_alloc(size_t bytes, void **out) {
@@ -981,23 +1182,6 @@ int wfl_get_stats(const wfl_engine *e, wfl_stats *out) {
     return WFL_OK;
 }
 
-int wfl_configure(wfl_engine *e, int threads, int smem_bytes, int ctas_per_sm) {
-    if (!e) return WFL_ERR_ARG;
-    if (threads) {
-        if (threads < 32 || threads > 1024 || threads % 32) { set_err(e, "threads must be a multiple of 32 in [32,1024]"); return WFL_ERR_ARG; }
-        e->threads = threads;
-    }
-    if (smem_bytes) {
-        if (smem_bytes < 0 || (size_t)smem_bytes + 2048 > e->smem_optin) { set_err(e, "smem_bytes too large"); return WFL_ERR_ARG; }
-        e->smem_bytes = smem_bytes & ~15;
-    }
-    if (ctas_per_sm) {
-        if (ctas_per_sm < 1 || ctas_per_sm > 32) { set_err(e, "ctas_per_sm out of range"); return WFL_ERR_ARG; }
-        e->ctas_per_sm = ctas_per_sm;
-    }
-    return WFL_OK;
-}
-
 int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int32_t *locus, double *score,
                               int64_t capacity) {
     if (!e) return WFL_ERR_ARG;
@@ -1010,30 +1194,16 @@ int64_t wfl_debug_gene_scores(wfl_engine *e, int64_t contig, int32_t *clade, int
     int32_t *dc, *dl;
     double *ds;
     long long *dn;
-    int64_t *wl;
-    char *slab;
     size_t cap = (size_t)std::max<int64_t>(capacity, 1);
     if ((rc = outbuf(e, e->ctr, 1, &ctr)) || (rc = outbuf(e, e->dbg[0], cap, &dc)) ||
         (rc = outbuf(e, e->dbg[1], cap, &dl)) || (rc = outbuf(e, e->dbg[2], cap, &ds)) ||
-        (rc = outbuf(e, e->dbg[3], 1, &dn)) || (rc = outbuf(e, e->work, 1, &wl)))
+        (rc = outbuf(e, e->dbg[3], 1, &dn)))
         return rc;
-    size_t slab_bytes = size_t(256) << 20;   // one CTA, generous
-    if ((rc = outbuf(e, e->slab, slab_bytes, &slab))) return rc;
     CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
     CU(cudaMemsetAsync(dn, 0, sizeof(long long), e->stream));
-    CU(cudaMemcpyAsync(wl, &contig, sizeof contig, cudaMemcpyHostToDevice, e->stream));
-    ScoreArgs a{};
-    a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
-    a.work_list = wl; a.n_work = 1; a.slab = slab; a.slab_bytes = slab_bytes; a.smem_bytes = e->smem_bytes;
-    a.plan_nmax = e->plan_nmax; a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
-    a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
-    a.plan_tree = e->use_tree ? static_cast<const TreeEntry *>(e->plan_tree.p) : nullptr;
-    a.dbg_contig = contig; a.dbg_clade = dc; a.dbg_locus = dl; a.dbg_score = ds; a.dbg_cap = capacity; a.dbg_count = dn;
-    if (e->mode != 0)
-        launch_score_kernel_warp(a, 1, e->stream);
-    else
-        launch_score_kernel(a, 1, e->threads, e->stream);
-    CU(cudaGetLastError());
+    // the exact pipeline over this one contig, with the level-0 dump switched on
+    if ((rc = launch_pipeline(e, ctr, nullptr, contig, 1, (size_t)(e->h_hit_off[contig + 1] - e->h_hit_off[contig]), 0, 16, contig)))
+        return rc;
     long long cnt = 0;
     CU(cudaMemcpyAsync(&cnt, dn, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));

@@ -28,6 +28,9 @@ struct DevBatch {
     const uint32_t *hit_sysmask;
     const int32_t *locus_start, *locus_end;
     const int8_t *locus_strand;
+    // compact wire format (wfl_packed_batch): 14 B/hit; null in the wide format
+    const uint16_t *hit_qstart16, *hit_qend16, *hit_tax16;
+    const uint8_t *hit_sysmask8;
 };
 
 // Result arrays on the device (wfl_results) plus the member staging pool.
@@ -50,11 +53,13 @@ struct DevOut {
 struct DevCounters {
     unsigned long long next_work;       // work-queue head
     unsigned long long mem_pool_used;   // staging pool bump pointer (may exceed capacity)
-    unsigned long long slab_need_max;   // max workspace bytes any contig asked for
-    unsigned long long n_overflow;      // contigs that overflowed their workspace
+    unsigned long long n_overflow;      // contigs that overflowed their workspace (status 1: replayed)
     unsigned long long n_runaway;
     unsigned long long n_badinput;      // contigs with a taxon index outside the taxonomy
     unsigned long long matched_pairs, groups, levels, pairs_tested, pairs_scored, smem_contigs;
+    unsigned long long n_fallback;      // contigs the fused fast-path kernel handed to the exact pipeline
+    unsigned long long guard_trips;     // ... of which because a rank comparison fell inside the guard band
+    unsigned long long refined_groups;  // gene scores recomputed exactly inside the fast kernel (near a threshold)
     unsigned long long phase_cycles[12];   // thread-0 clock64 deltas per phase (profiling aid)
 };
 
@@ -70,44 +75,45 @@ struct DevParams {
 // distinct m/8 values (ascending, 0 = unused / memo disabled).
 struct PlanEntry {
     uint32_t off, nleaf, k8;
-    uint32_t toff, nsz;   // node-size table of the same tree (TreeEntry[nsz], ascending size, root last)
 };
 
-// One distinct node size of the pairwise split tree: a node of `size` > 128 elements splits into
-// nodes li / ri (indices into the same table); li == ri == 255 marks a leaf (size <= 128).
-struct TreeEntry {
-    uint16_t size;
-    uint8_t li, ri;
+// ---- fused fast-path kernel (wfl_fast.cu) ---------------------------------------------------
+// Layout of one warp's shared-memory slice (byte offsets) and its capacities; computed on the host.
+struct FastCfg {
+    int slice_bytes;
+    int Kcap;      // records of one locus
+    int cmask;     // clade hash slots - 1 (power of two)
+    int Tcap;      // distinct clades per level
+    int Ncap;      // (clade, locus) groups per level
+    int Scap;      // two-clade pairs that pass the mask prefilter
+    int o_llo, o_llen, o_lraw, o_lstr, o_goff, o_maxv, o_unk;
+    int o_bv, o_bab, o_bt, o_bcl, o_bh;
+    int o_hkey, o_hval, o_clid, o_mk0, o_mk1, o_mk2, o_cur, o_gscore, o_gt;
 };
 
-struct ScoreArgs {
+struct FastArgs {
     DevBatch b;
     DevTax t;
     DevOut o;
     DevParams P;
     DevCounters *ctr;
-    const int64_t *work_list;   // optional list of contig indices (replays); null = 0..n-1
-    int64_t n_work;
-    int64_t work_base;          // first contig of this launch when work_list is null
-    char *slab;                 // per-CTA global workspace, slab_bytes each
-    size_t slab_bytes;
-    int smem_bytes;             // dynamic shared memory per CTA
-    // pairwise-sum leaf plans for every gene length 1..plan_nmax (host-built, L2-resident)
+    FastCfg cfg;
+    unsigned long long *wq;        // work-queue head of this launch
+    int64_t n_work, work_base;     // contig range ...
+    const int *work_list;          // ... or explicit list
+    int *fb_list;                  // fallback list (ctr->n_fallback entries): contigs for the exact pipeline
+    const int *anc;                // [anc_rows][n_nodes]: l-th ancestor of every node (row 0 = identity)
+    int anc_rows;
+    double guard;                  // guard band of the decision compares (1e-12)
     int plan_nmax;
-    const PlanEntry *plan_index;   // [plan_nmax + 1]
+    const PlanEntry *plan_index;
     const uint16_t *plan_data;
-    const TreeEntry *plan_tree;
-    // test hook: dump the level-0 gene scores of one contig as COO triples
-    long long dbg_contig;       // -1 = off
-    int32_t *dbg_clade, *dbg_locus;
-    double *dbg_score;
-    long long dbg_cap;
-    long long *dbg_count;
+    char *scratch;                 // 16 * Kcap bytes per resident warp (exact recomputation of near-threshold groups)
 };
-
-void launch_score_kernel(const ScoreArgs &a, int grid, int threads, cudaStream_t s);       // v1: CTA per contig
-void launch_score_kernel_warp(const ScoreArgs &a, int grid, cudaStream_t s);             // v2: warp per contig
-
+int fast_layout(FastCfg &F, int Kcap, int Ccap, int Tcap, int Ncap, bool annotations);
+int fast_warps_per_cta();
+int fast_ctas_per_sm(const FastCfg &F, bool packed, size_t smem_per_sm);
+cudaError_t launch_fast(const FastArgs &a, bool packed, int grid, cudaStream_t s);
 
 // ---- multi-kernel pipeline (wfl_pipeline.cu) ------------------------------------------------
 enum { PIPE_DONE = 0, PIPE_ACTIVE = 1 };
@@ -148,7 +154,8 @@ struct PipeArgs {
     DevParams P;
     DevCounters *ctr;
     unsigned long long *wq;        // work-queue head of THIS launch
-    int64_t n_work, work_base;     // prepare: contig range of the sub-batch
+    int64_t n_work, work_base;     // prepare: contig range of the sub-batch ...
+    const int *work_list;          // ... or an explicit list of n_work contig indices (replays, fast-path fallbacks)
     char *pool;                    // workspace pool of the sub-batch
     unsigned long long *pool_used;
     unsigned long long pool_cap;
@@ -158,8 +165,7 @@ struct PipeArgs {
     int plan_nmax;
     const PlanEntry *plan_index;
     const uint16_t *plan_data;
-    const TreeEntry *plan_tree;
-    K2Desc *k2_desc;               // null: K2 per contig (wfl_pipe_scores)
+    K2Desc *k2_desc;
     unsigned int *k2_order;
     unsigned int *k2_keys;         // sort key of every descriptor (compact copy for the counting sort)
     unsigned long long k2_cap;
@@ -173,7 +179,6 @@ struct PipeArgs {
 
 void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s);
-void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_masks(const PipeArgs &a, int grid, cudaStream_t s);
 void launch_pipe_k2sort(const PipeArgs &a, int grid, cudaStream_t s);   // scan + scatter
 void launch_pipe_k2(const PipeArgs &a, int grid, cudaStream_t s);

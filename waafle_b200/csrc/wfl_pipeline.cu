@@ -1,30 +1,37 @@
-// GENERATED by tools/gen_pipeline.py from wfl_score_warp.cu -- do not edit by hand.
-//
-// The orgscorer path as a pipeline of seven small kernels (same per-phase code as the monolithic
-// warp-per-contig kernel, one warp per contig in every kernel):
+// The EXACT orgscorer path as a pipeline of small kernels, one warp per contig in every kernel.  It reproduces
+// numpy's pairwise summation bit for bit; it scores the contigs the fused fast-path kernel (wfl_fast.cu) hands
+// back (guard band tripped, or too large for its shared-memory slice) and everything under WFL_K2=exact.
 //
 //   wfl_pipe_prepare : K1 match + record emission, K3 annotations, base order, distinct-clade table
 //                      (the only kernel that streams the hit SoA from HBM)
 //   wfl_pipe_regroup : K5 regroup (stable multisplit by clade rank, group table)
-//   wfl_pipe_scores  : K2 envelope integrals (gene score per (clade, locus) group)
+//   wfl_pipe_k2hist / k2scan / k2scatter / k2 : K2 envelope integrals (gene score per (clade, locus) group) over
+//                      the sub-batch's group list, counting-sorted so that a warp's lanes share a leaf plan
 //   wfl_pipe_masks   : K4 weak loci, clade rows + gene bitmasks
 //   wfl_pipe_one     : K6 one-clade search + meld; unresolved contigs go to the two-clade list
 //   wfl_pipe_two     : K7/K8 two-clade search, meld, LGT filters; undecided contigs go to the lift list
 //   wfl_pipe_lift    : K9 stop-or-lift (K5 lift of the clade table; next level's list)
 //
-// regroup/scores/masks/one/two/lift are launched once per taxonomy level over device-side work lists (no host sync in
+// regroup/K2/masks/one/two/lift are launched once per taxonomy level over device-side work lists (no host sync in
 // the level loop; an empty list makes the launch a no-op).  Between kernels a contig's state lives
 // in a global workspace pool (regions A: loci, B: records + clade table, C: per-level arrays), carved
-// by the same deterministic bump arena in every kernel.  Why: the monolithic kernel is bound by
-// instruction fetch (profiles/r1_final_score_kernel_ncu.txt); here every kernel's hot code fits the
-// SM instruction cache and all warps of an SM run the same phase.
+// by the same deterministic bump arena in every kernel.  Why small kernels: as one kernel this code is bound
+// by instruction fetch (profiles/r1_final_score_kernel_ncu.txt); here every kernel's hot code fits the SM
+// instruction cache and all warps of an SM run the same phase.
 #include "wfl_warp_common.cuh"
 
 namespace wfl {
 
 namespace {
 
-#define PH(i) do { } while (0)
+// per-phase cycle counters (wfl_stats.phase_cycles): compiled in only with -DWFL_PROFILE
+#ifdef WFL_PROFILE
+#define PH_BEGIN const long long t_start = clock64()
+#define PH_END(i) do { if (lane == 0) atomicAdd(&a.ctr->phase_cycles[i], (unsigned long long)(clock64() - t_start)); } while (0)
+#else
+#define PH_BEGIN do { } while (0)
+#define PH_END(i) do { } while (0)
+#endif
 
 #ifndef WFL_PIPE_CPSM
 #define WFL_PIPE_CPSM 32   // resident single-warp CTAs per SM the pipeline kernels are compiled for
@@ -137,7 +144,6 @@ struct ContigOut {
 __device__ __noinline__ void write_result(const PipeArgs &a, long long c, const ContigOut &r) {
     if (r.status == 1) {
         atomicAdd(&a.ctr->n_overflow, 1ull);
-        atomicMax(&a.ctr->slab_need_max, 1ull << 20);
     }
     if (r.status == 2) atomicAdd(&a.ctr->n_runaway, 1ull);
     if (r.status == 3) atomicAdd(&a.ctr->n_badinput, 1ull);
@@ -216,11 +222,11 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
         long long c = -1;
         if (lane == 0) {
             unsigned long long w = atomicAdd(a.wq, 1ull);
-            c = (long long)w < a.n_work ? a.work_base + (long long)w : -1;
+            c = (long long)w < a.n_work ? (a.work_list ? (long long)a.work_list[w] : a.work_base + (long long)w) : -1;
         }
         c = __shfl_sync(FULL, c, 0);
         if (c < 0) break;
-        const long long t_start = clock64();
+        PH_BEGIN;
         const long long h0 = a.b.hit_off[c], l0 = a.b.locus_off[c];
         const int H = (int)(a.b.hit_off[c + 1] - h0), Graw = (int)(a.b.locus_off[c + 1] - l0);
         RESULT_LOCALS
@@ -290,11 +296,12 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
                 int hmin = 0, hmax = 0;
                 signed char hs = 0;
                 if (h < H) {
-                    hok = a.b.hit_scov[h0 + h] >= P.p.min_scov;   // waafle_orgscorer.py:362
-                    int q1 = a.b.hit_qstart[h0 + h], q2 = a.b.hit_qend[h0 + h];
+                    hok = hit_scov_ok(a.b, h0 + h, P.p.min_scov);   // waafle_orgscorer.py:362
+                    int q1, q2;
+                    hit_span(a.b, h0 + h, q1, q2);
                     hmin = min(q1, q2);
                     hmax = max(q1, q2);
-                    hs = a.b.hit_strand[h0 + h];
+                    hs = hit_strand_of(a.b, h0 + h);
                 }
                 if (!__any_sync(FULL, hok)) continue;
 #pragma unroll 1
@@ -342,13 +349,8 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
                     const int len = l_len[i];
                     if (len <= a.plan_nmax) {
                         const PlanEntry pe = a.plan_index[len];
-                        if (a.plan_tree != nullptr) {   // node-size table (tree walk); nleaf < 0 flags it
-                            l_plan[i] = reinterpret_cast<const u16 *>(a.plan_tree + pe.toff);
-                            l_nleaf[i] = -(int)pe.nsz;
-                        } else {
-                            l_plan[i] = a.plan_data + pe.off;
-                            l_nleaf[i] = (int)pe.nleaf;
-                        }
+                        l_plan[i] = a.plan_data + pe.off;
+                        l_nleaf[i] = (int)pe.nleaf;
                         l_k8[i] = pe.k8;
                     } else {
                         u16 *dst = plan_fb + l_nleaf[i];
@@ -369,20 +371,21 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
                     double sc = 0.0;
                     u32 sys = 0;
                     if (h < H) {
-                        hok = a.b.hit_scov[h0 + h] >= P.p.min_scov;
-                        int q1 = a.b.hit_qstart[h0 + h], q2 = a.b.hit_qend[h0 + h];
+                        hok = hit_scov_ok(a.b, h0 + h, P.p.min_scov);
+                        int q1, q2;
+                        hit_span(a.b, h0 + h, q1, q2);
                         hmin = min(q1, q2);
                         hmax = max(q1, q2);
-                        hs = a.b.hit_strand[h0 + h];
+                        hs = hit_strand_of(a.b, h0 + h);
                     }
                     if (!__any_sync(FULL, hok)) continue;
                     if (hok) {
-                        cl = a.b.hit_taxon[h0 + h];
+                        cl = hit_taxon_of(a.b, h0 + h);
                         if ((u32)cl >= (u32)tax.n_nodes) { cl = tax.root; bad_input = true; }
 #pragma unroll 1
                         for (int j = 0; j < P.p.jump_taxonomy; ++j) cl = tax.parent[cl];
                         sc = a.b.hit_score[h0 + h];
-                        if (S > 0) sys = a.b.hit_sysmask[h0 + h];
+                        if (S > 0) sys = hit_sysmask_of(a.b, h0 + h);
                     }
 #pragma unroll 1
                     for (int i = 0; i < G; ++i) {
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
                     // K3 phase 2: the LAST hit (file order) attaining the max wins (:389, '>=')
 #pragma unroll 1
                     for (int r = lane; r < M; r += 32) {
-                        u32 ms = a.b.hit_sysmask[h0 + r_hit[r]];
+                        u32 ms = hit_sysmask_of(a.b, h0 + r_hit[r]);
                         double sc = r_v[r];
                         if (ms && sc >= P.ann_thr) {
                             u64 sb = dbits(sc);
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
             if (overflow) r_status = 1;
             EMIT_RESULT(r_status);
         }
-        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[0], (unsigned long long)(clock64() - t_start));
+        PH_END(0);
         __syncwarp();
     }
 }
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_regro
     for (;;) {
         const long long c = pop_work(a.wq, a.list_act, a.cnt_act, lane);
         if (c < 0) break;
-        const long long t_start = clock64();
+        PH_BEGIN;
         OPEN_CONTIG
         RESULT_LOCALS
         bool overflow = false;
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_regro
 #pragma unroll 1
             for (int i = lane; i < G; i += 32) maxb[i] = dbits(0.0);
             __syncwarp();
-            if (a.k2_desc != nullptr) {
+            {
                 // ---- K2 work items: one descriptor per group with records, appended to the sub-batch's list
                 const int nreal = spike ? Ngrp - G : Ngrp;   // the G spiked Unknown rows carry no records
                 // reserve nreal slots with ONE atomic add (a compare-and-swap loop on this counter serialises the
@@ -758,7 +761,6 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_regro
         if (lane == 0) {
             atomicAdd(&a.ctr->groups, (unsigned long long)n_groups);
             atomicAdd(&a.ctr->levels, 1ull);
-            atomicAdd(&a.ctr->phase_cycles[2], (unsigned long long)(clock64() - t_start));
         }
         if (overflow) {
             EMIT_RESULT(1);
@@ -771,94 +773,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_regro
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 2b: K2 -- envelope integral of every (clade, locus) group, numpy-pairwise-exact
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_scores(const PipeArgs a) {
-    const int lane = threadIdx.x;
-    const DevParams &P = a.P;
-    const DevTax &tax = a.t;
-    const int S = P.p.n_systems;
-#pragma unroll 1
-    for (;;) {
-        const long long c = pop_work(a.wq, a.list_act, a.cnt_act, lane);
-        if (c < 0) break;
-        if (a.ctg[c].state != PIPE_ACTIVE) continue;
-        const long long t_start = clock64();
-        OPEN_CONTIG
-        const int Ngrp = cx.Ngrp, ng = cx.ng;
-        DECL_CUR
-        DECL_GROUPS
-        (void)cur; (void)gs; (void)T; (void)lifts; (void)l_raw; (void)l0; (void)ign; (void)um; (void)r_t; (void)r_loc;
-            // ---- K2: envelope integral per group, numpy-pairwise-exact ----------------------
-            // groups are visited multi-record groups first, then single-record ones, locus-major inside
-            // each class: lanes of a warp then walk the same leaf plan and meet groups of similar
-            // envelope complexity (leaves with several run boundaries are the expensive, divergent part)
-            {
-                int *gkey = reinterpret_cast<int *>(g_score);   // g_score is written only below
-#pragma unroll 1
-                for (int g = lane; g < Ngrp; g += 32)
-                    gkey[g] = g_loc[g] + ((g_rs[g] >= 0 && g_re[g] - g_rs[g] >= 2) ? 0 : G);
-                __syncwarp();
-                warp_multisplit(Ngrp, 2 * G, gkey, nullptr, gcur, g_perm);
-            }
-            __syncwarp();
-#if WFL_K2_CONV
-#pragma unroll 1
-            for (int base = 0; base < Ngrp; base += 32) {
-                // all 32 lanes call group_mean_warp together (it re-converges them before every leaf)
-                const int gi = base + lane;
-                int g = 0, rs = -1, re = 0, t = 0, loc = 0, nleaf = 0;
-                if (gi < Ngrp) {
-                    g = g_perm[gi];
-                    rs = g_rs[g];
-                    if (rs >= 0) {
-                        t = g_t[g];
-                        loc = g_loc[g];
-                        re = g_re[g];
-                        nleaf = l_nleaf[loc];
-                    }
-                }
-                double sc;
-                if (a.plan_tree != nullptr) {   // experimental tree walk: per lane
-                    sc = rs >= 0 ? group_mean(s_a, s_b, s_v, rs, re, l_len[loc], true, l_k8[loc],
-                                              l_plan[loc], nleaf) : 0.0;
-                } else {
-                    sc = group_mean_warp(s_a, s_b, s_v, max(rs, 0), re, l_len[loc], true, l_k8[loc],
-                                         l_plan[loc], rs >= 0 ? nleaf : 0);
-                }
-                if (rs >= 0) {
-                    g_score[g] = sc;
-                    if (cl_id[t] != tax.unknown)   // waafle_orgscorer.py:409-411
-                        atomicMax(&maxb[loc], dbits(sc));
-                }
-            }
-#else
-#pragma unroll 1
-            for (int base = 0; base < Ngrp; base += 32) {
-                int gi = base + lane;
-                if (gi < Ngrp) {
-                    int g = g_perm[gi];
-                    int rs = g_rs[g];
-                    if (rs >= 0) {
-                        const int t = g_t[g], loc = g_loc[g];
-                        const int re = g_re[g];
-                        double sc = group_mean(s_a, s_b, s_v, rs, re, l_len[loc], true, l_k8[loc],
-                                               l_plan[loc], l_nleaf[loc]);
-                        g_score[g] = sc;
-                        if (cl_id[t] != tax.unknown)   // waafle_orgscorer.py:409-411
-                            atomicMax(&maxb[loc], dbits(sc));
-                    }
-                }
-            }
-#endif
-            __syncwarp();
-        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(clock64() - t_start));
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernels 2b': K2 over the sub-batch's GLOBAL group list.  Counting sort of the descriptors by
+// kernels 2b: K2 (envelope integral of every (clade, locus) group, numpy-pairwise-exact) over the sub-batch's GLOBAL group list.  Counting sort of the descriptors by
 // (leaf count, record-count class), then lane per group: the lanes of a warp walk the same leaf plan
 // whatever contig their group belongs to (per contig, lanes met different plans and a partly filled last
 // round: 11 of 32 threads active per instruction).
@@ -930,7 +845,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_k2(const PipeArgs 
         if (lane == 0) base = atomicAdd(&a.k2_meta->take, 32ull);
         base = __shfl_sync(FULL, base, 0);
         if (base >= n) break;
-        const long long t_start = clock64();
+        PH_BEGIN;
         const unsigned long long i = base + lane;
         if (i < n) {
             const K2Desc d = a.k2_desc[a.k2_order[i]];
@@ -949,7 +864,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_k2(const PipeArgs 
             if (d.maxb != nullptr) atomicMax(d.maxb, dbits(sc));   // waafle_orgscorer.py:409-411
             }
         }
-        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[3], (unsigned long long)(clock64() - t_start));
+        PH_END(3);
         __syncwarp();
     }
 }
@@ -968,7 +883,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_masks
         const long long c = pop_work(a.wq, a.list_act, a.cnt_act, lane);
         if (c < 0) break;
         if (a.ctg[c].state != PIPE_ACTIVE) continue;
-        const long long t_start = clock64();
+        PH_BEGIN;
         OPEN_CONTIG
         RESULT_LOCALS
         const int Ngrp = cx.Ngrp, ng = cx.ng, nlt = cx.nlt;
@@ -1057,7 +972,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_masks
             const Level &L = *Lp;
             cont_ok = true;
         }
-        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[4], (unsigned long long)(clock64() - t_start));
+        PH_END(4);
         if (overflow) {
             EMIT_RESULT(1);
         } else if (!cont_ok) {
@@ -1084,7 +999,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_one(c
         const long long c = pop_work(a.wq, a.list_act, a.cnt_act, lane);
         if (c < 0) break;
         if (a.ctg[c].state != PIPE_ACTIVE) continue;
-        const long long t_start = clock64();
+        PH_BEGIN;
         OPEN_CONTIG
         RESULT_LOCALS
         const int Ngrp = cx.Ngrp, ng = cx.ng;
@@ -1175,7 +1090,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_one(c
             int slot = atomicAdd(a.cnt_two, 1);
             a.list_two[slot] = (int)c;
         }
-        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[5], (unsigned long long)(clock64() - t_start));
+        PH_END(5);
         __syncwarp();
     }
 }
@@ -1193,7 +1108,7 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
     for (;;) {
         const long long c = pop_work(a.wq, a.list_two, a.cnt_two, lane);
         if (c < 0) break;
-        const long long t_start = clock64();
+        PH_BEGIN;
         OPEN_CONTIG
         RESULT_LOCALS
         const int Ngrp = cx.Ngrp, ng = cx.ng, nu = cx.nu, t_unk = cx.t_unk, hasroot = cx.hasroot;
@@ -1412,7 +1327,6 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
         if (lane == 0) {
             if (n_ptest) atomicAdd(&a.ctr->pairs_tested, (unsigned long long)n_ptest);
             if (n_pscore) atomicAdd(&a.ctr->pairs_scored, (unsigned long long)n_pscore);
-            atomicAdd(&a.ctr->phase_cycles[6], (unsigned long long)(clock64() - t_start));
         }
         if (overflow) {
             r_call = WFL_CALL_UNCLASSIFIED;
@@ -1441,7 +1355,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_lift(
     for (;;) {
         const long long c = pop_work(a.wq, a.list_lift, a.cnt_lift, lane);
         if (c < 0) break;
-        const long long t_start = clock64();
+        PH_BEGIN;
         OPEN_CONTIG
         RESULT_LOCALS
         const int Ngrp = cx.Ngrp, ng = cx.ng, nu = cx.nu, t_unk = cx.t_unk, hasroot = cx.hasroot;
@@ -1539,7 +1453,7 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_lift(
             ++lifts;
             lifted = true;
         }
-        if (lane == 0) atomicAdd(&a.ctr->phase_cycles[7], (unsigned long long)(clock64() - t_start));
+        PH_END(7);
         if (overflow) {
             r_call = WFL_CALL_UNCLASSIFIED;
             r_na = r_nb = 0;
@@ -1558,17 +1472,16 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_lift(
     }
 }
 
-// Contigs still on the work list after the last level (deeper than the host's level bound): hand
-// them to the monolithic kernel by marking them for replay.
+// Contigs still on the work list after the last level: every lift moves the shallowest clade one level up, so
+// max depth + 1 levels always suffice -- anything left is runaway recursion (waafle_orgscorer.py:580-581).
 __global__ void wfl_pipe_leftover(const PipeArgs a) {
     const int n = *a.cnt_act;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = a.list_act[i];
-        a.o.status[c] = 1;
+        a.o.status[c] = 2;
         a.o.call[c] = WFL_CALL_UNCLASSIFIED;
         a.o.n_mem_a[c] = a.o.n_mem_b[c] = 0;
-        atomicAdd(&a.ctr->n_overflow, 1ull);
-        atomicMax(&a.ctr->slab_need_max, 1ull << 20);
+        atomicAdd(&a.ctr->n_runaway, 1ull);
     }
 }
 
@@ -1577,7 +1490,6 @@ __global__ void wfl_pipe_leftover(const PipeArgs a) {
 // ---------------------------------------------------------------------------------------------
 void launch_pipe_prepare(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_prepare<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_regroup(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_regroup<<<grid / WFL_PIPE_CPSM * WFL_LAT_CPSM, 32 * WFL_LAT_WPC, 0, s>>>(a); }
-void launch_pipe_scores(const PipeArgs &a, int grid, cudaStream_t s) { wfl_pipe_scores<<<grid, 32, 0, s>>>(a); }
 void launch_pipe_k2sort(const PipeArgs &a, int grid, cudaStream_t s) {
     wfl_pipe_k2hist<<<grid / 8 + 1, 256, 0, s>>>(a);
     wfl_pipe_k2scan<<<1, K2_KEYS, 0, s>>>(a);

@@ -1,5 +1,6 @@
-// Warp-synchronous device helpers shared by the warp-per-contig kernels (wfl_score_warp.cu: the
-// monolithic kernel; wfl_pipeline.cu: the same phases as separate, instruction-cache-sized kernels).
+// Warp-synchronous device helpers shared by the warp-per-contig kernels (wfl_pipeline.cu: the exact path as
+// instruction-cache-sized phase kernels; wfl_fast.cu: the fused shared-memory fast path, which calls the exact
+// K2 code below for gene scores that land inside its guard band).
 #pragma once
 
 #include "wfl_device.cuh"
@@ -17,12 +18,6 @@ constexpr int MAXDEPTH = 28;   // pairwise tree depth for n < 2^31
 constexpr int BITMAP_MAX_WORDS = 1024;   // taxonomies up to 32768 nodes use the bitmap clade table
 #ifndef WFL_K2_TWO
 #define WFL_K2_TWO 1     // closed form for leaves with two run boundaries
-#endif
-#ifndef WFL_K2_CONV
-#define WFL_K2_CONV 0    // all lanes walk the leaf plan together, convergence barrier before every leaf
-#endif
-#ifndef WFL_K2_TREE
-#define WFL_K2_TREE 1    // experimental tree walk (WFL_K2=tree) compiled in
 #endif
 constexpr int RMAX = 6;        // envelope runs handled per mixed leaf before the per-site fallback
 
@@ -60,6 +55,25 @@ struct Arena {
     template <class T>
     __device__ __forceinline__ T *get(size_t n) { return static_cast<T *>(raw(n * sizeof(T))); }
 };
+
+// ---- hit columns in either wire format (wide wfl_batch / compact wfl_packed_batch) -----------------
+__device__ __forceinline__ void hit_span(const DevBatch &b, long long h, int &q1, int &q2) {
+    if (b.hit_tax16) { q1 = b.hit_qstart16[h]; q2 = b.hit_qend16[h]; }
+    else { q1 = b.hit_qstart[h]; q2 = b.hit_qend[h]; }
+}
+// scov_modified >= --min-scov (waafle_orgscorer.py:362); the compact format carries the host's verdict in bit 15
+__device__ __forceinline__ bool hit_scov_ok(const DevBatch &b, long long h, double min_scov) {
+    return b.hit_tax16 ? (b.hit_tax16[h] & 0x8000u) != 0u : b.hit_scov[h] >= min_scov;
+}
+__device__ __forceinline__ signed char hit_strand_of(const DevBatch &b, long long h) {
+    return b.hit_tax16 ? ((b.hit_tax16[h] & 0x4000u) ? '-' : '+') : b.hit_strand[h];
+}
+__device__ __forceinline__ int hit_taxon_of(const DevBatch &b, long long h) {
+    return b.hit_tax16 ? (int)(b.hit_tax16[h] & 0x3fffu) : b.hit_taxon[h];
+}
+__device__ __forceinline__ u32 hit_sysmask_of(const DevBatch &b, long long h) {
+    return b.hit_tax16 ? (u32)b.hit_sysmask8[h] : b.hit_sysmask[h];
+}
 
 // ---- warp primitives -----------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -495,116 +509,10 @@ __device__ __forceinline__ double mixed_leaf(Site &s, int m) {
     return res;
 }
 
-#if WFL_K2_TREE
-// Tree walk of the same sum.  numpy's split depends only on the node size, so the tree of an n-element
-// sum has a handful of distinct node sizes (<= 23 for n <= 16384; host-built table, children by index).
-// A node that lies inside ONE envelope run is a sum over a constant array: its value C(size, v) is
-// computed once per run for every table entry (leaves by add chain, inner nodes C(l) + C(r)) and whole
-// subtrees are skipped; only the leaves that straddle a run boundary are evaluated per column.
-__device__ __noinline__ double group_mean_tree(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
-                                               bool sorted, const TreeEntry *te, int nsz) {
-    Site s;
-    s.ra = ra; s.rb = rb; s.rv = rv;
-    s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
-    s.k8[0] = s.k8[1] = s.k8[2] = s.k8[3] = 0;
-    s.pos = 0;
-    s.run_end = 0;
-    s.memo_ok = false;
-    double Cv[24];
-    int cv_run = -1;   // Cv holds C(size, run_v) of the run that ends at cv_run
-    unsigned char sidx[12], sst[12];
-    int spos[12];
-    double sacc[12];
-    int sp = 0;
-    sidx[0] = (unsigned char)(nsz - 1);
-    spos[0] = 0;
-    sst[0] = 0;
-    double ret = 0.0;
-    bool returning = false;
-#pragma unroll 1
-    for (;;) {
-        if (!returning) {
-            const TreeEntry e = te[sidx[sp]];
-            const int m = e.size, p = spos[sp];
-            s.pos = p;   // nodes are visited left to right
-            if (s.pos >= s.run_end) s.advance();
-            if (s.run_end - p >= m) {
-                // the node lies inside one run
-                if (s.run_v == 0.0) {
-                    ret = 0.0;
-                } else {
-                    if (cv_run != s.run_end) {
-                        const double v = s.run_v;
-                        double c = v;
-                        int ck = 1;
-#pragma unroll 1
-                        for (int j = 0; j < nsz; ++j) {
-                            const TreeEntry ej = te[j];
-                            double r;
-                            if (ej.li == 255) {
-                                const int mm = ej.size;
-                                if (mm < 8) {
-                                    r = 0.0;
-#pragma unroll 1
-                                    for (int i = 0; i < mm; ++i) r += v;
-                                } else {
-                                    const int k = mm >> 3;   // ascending with j: extend the add chain S_k(v)
-#pragma unroll 1
-                                    for (; ck < k; ++ck) c += v;
-                                    r = 8.0 * c;             // eight equal lanes: the fold is exact
-#pragma unroll 1
-                                    for (int i = 0; i < (mm & 7); ++i) r += v;
-                                }
-                            } else {
-                                r = Cv[ej.li] + Cv[ej.ri];
-                            }
-                            Cv[j] = r;
-                        }
-                        cv_run = s.run_end;
-                    }
-                    ret = Cv[sidx[sp]];
-                }
-                returning = true;
-                if (--sp < 0) break;
-            } else if (e.li == 255) {
-                ret = mixed_leaf(s, m);   // a leaf that straddles a run boundary
-                returning = true;
-                if (--sp < 0) break;
-            } else {
-                sst[sp] = 1;
-                ++sp;
-                sidx[sp] = e.li;
-                spos[sp] = p;
-                sst[sp] = 0;
-            }
-        } else if (sst[sp] == 1) {
-            const TreeEntry e = te[sidx[sp]];
-            sacc[sp] = ret;
-            sst[sp] = 2;
-            const int p = spos[sp] + te[e.li].size;
-            ++sp;
-            sidx[sp] = e.ri;
-            spos[sp] = p;
-            sst[sp] = 0;
-            returning = false;
-        } else {
-            ret = sacc[sp] + ret;
-            if (--sp < 0) break;
-        }
-    }
-    return ret / (double)n;
-}
-
-#endif
-
 // np.mean of the group's site array (waafle_orgscorer.py:403) without materialising it.
 // ra/rb/rv[rs..re) are the group's records (in descending score order if `sorted`).
 __device__ __noinline__ double group_mean(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
                                           bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
-#if WFL_K2_TREE
-    if (nleaf < 0)   // tree mode: `plan` is the node-size table of this gene length
-        return group_mean_tree(ra, rb, rv, rs, re, n, sorted, reinterpret_cast<const TreeEntry *>(plan), -nleaf);
-#endif
     Site s;
     s.ra = ra; s.rb = rb; s.rv = rv;
     s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
@@ -626,37 +534,76 @@ __device__ __noinline__ double group_mean(const int *ra, const int *rb, const do
     return st[0] / (double)n;
 }
 
-#if WFL_K2_CONV
-// The same sum, called by ALL 32 lanes of a warp at once (a lane without a group passes nleaf = 0); the lanes
-// meet at a convergence barrier before every leaf.
-__device__ __noinline__ double group_mean_warp(const int *ra, const int *rb, const double *rv, int rs, int re, int n,
-                                               bool sorted, u32 k8pack, const u16 *plan, int nleaf) {
-    Site s;
-    s.ra = ra; s.rb = rb; s.rv = rv;
-    s.rs = rs; s.re = re; s.n = n; s.sorted = sorted;
-    s.k8[0] = (u8)k8pack; s.k8[1] = (u8)(k8pack >> 8); s.k8[2] = (u8)(k8pack >> 16); s.k8[3] = (u8)(k8pack >> 24);
-    s.pos = 0;
-    s.run_end = 0;
-    s.memo_ok = false;
-    double st[MAXDEPTH];
-    int sp = 0;
-    st[0] = 0.0;
-    const int nmax = __reduce_max_sync(0xffffffffu, nleaf);
+// ---- closed-form envelope integral (fast path, wfl_fast.cu) ----
+// The records of a group live in a per-locus buffer: bv[r] score (>= 0), bab[r] python slice a | b << 16, visited through
+// the order array bord[rs..re).
+// Generic envelope integral of one group (records q in [rs, re) of the locus buffer, via bord): sweep over the
+// distinct endpoints.  Cold: only groups whose better hits leave a gap.
+__device__ __noinline__ double group_integral_general(const double *bv, const u32 *bab, const u16 *bord, int rs, int re) {
+    double sum = 0.0;
 #pragma unroll 1
-    for (int l = 0; l < nmax; ++l) {
-        __syncwarp();
-        if (l < nleaf) {
-            const int e = plan[l], m = e & 0xff, nadd = e >> 8;
-            if (s.pos >= s.run_end) s.advance();
-            double val = (s.run_end - s.pos >= m) ? const_leaf(s, m) : mixed_leaf(s, m);
+    for (int e2 = 2 * rs; e2 < 2 * re; ++e2) {
+        const u32 abq = bab[bord[e2 >> 1]];
+        const int e = (e2 & 1) ? (int)(abq >> 16) : (int)(abq & 0xffffu);
+        bool dup = false;
+        int nx = 0x7fffffff;
+        double mx = 0.0;
 #pragma unroll 1
-            for (int q = 0; q < nadd; ++q) val = st[--sp] + val;
-            st[sp++] = val;
+        for (int q = rs; q < re; ++q) {
+            const int r = bord[q];
+            const u32 ab = bab[r];
+            const int a = (int)(ab & 0xffffu), b = (int)(ab >> 16);
+            if (a <= e && e < b) mx = fmax(mx, bv[r]);
+            if (a > e) nx = min(nx, a);
+            if (b > e) nx = min(nx, b);
+            dup |= (a == e && 2 * q < e2) || (b == e && 2 * q + 1 < e2);
         }
+        if (!dup && mx > 0.0 && nx != 0x7fffffff) sum += mx * (double)(nx - e);
     }
-    return st[0] / (double)n;
+    return sum;
 }
-#endif
+
+// Closed-form envelope integral of a group with >= 2 records: pick records in descending score order (ties: buffer
+// order), keep the union of the picked intervals as ONE interval [ua, ub) and add v * (newly covered sites).  Stops as
+// soon as the union covers the hull of the group.  A picked interval that leaves a gap -> generic sweep.
+__device__ __forceinline__ double group_integral(const double *bv, const u32 *bab, const u16 *bord, int rs, int re) {
+    double vlast = 1e300;   // above any score
+    int qlast = -1, ua = 0, ub = 0, hull_a = 0x7fffffff, hull_b = 0;
+    double sum = 0.0;
+#pragma unroll 1
+    for (int pick = 0;; ++pick) {
+        double bvv = -1.0;
+        int bq = -1;
+#pragma unroll 1
+        for (int q = rs; q < re; ++q) {
+            const int r = bord[q];
+            const double v = bv[r];
+            const bool el = v < vlast || (v == vlast && q > qlast);
+            if (el && v > bvv) { bvv = v; bq = q; }
+            if (pick == 0) {
+                const u32 ab = bab[r];
+                hull_a = min(hull_a, (int)(ab & 0xffffu));
+                hull_b = max(hull_b, (int)(ab >> 16));
+            }
+        }
+        if (bq < 0 || !(bvv > 0.0)) break;
+        const u32 ab = bab[bord[bq]];
+        const int a = (int)(ab & 0xffffu), b = (int)(ab >> 16);
+        if (pick == 0) {
+            ua = a; ub = b;
+            sum = bvv * (double)(b - a);
+        } else {
+            if (a > ub || b < ua) return group_integral_general(bv, bab, bord, rs, re);
+            sum += bvv * (double)(max(0, ua - a) + max(0, b - ub));
+            ua = min(ua, a);
+            ub = max(ub, b);
+        }
+        vlast = bvv;
+        qlast = bq;
+        if (ua <= hull_a && ub >= hull_b) break;
+    }
+    return sum;
+}
 
 // K2-HOST-END
 

@@ -20,11 +20,15 @@ c_u32p = ctypes.POINTER(ctypes.c_uint32)
 c_f64p = ctypes.POINTER(ctypes.c_double)
 c_i8p = ctypes.POINTER(ctypes.c_int8)
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_u16p = ctypes.POINTER(ctypes.c_uint16)
 
 EXPORTS = ["wfl_abi_version", "wfl_device_count", "wfl_create", "wfl_destroy", "wfl_last_error",
-           "wfl_set_params", "wfl_set_taxonomy", "wfl_score_batch", "wfl_upload_batch",
-           "wfl_run_resident", "wfl_download_results", "wfl_get_stats", "wfl_configure",
-           "wfl_debug_gene_scores", "wfl_host_alloc", "wfl_host_free"]
+           "wfl_set_params", "wfl_set_taxonomy", "wfl_score_batch", "wfl_score_packed", "wfl_upload_batch",
+           "wfl_upload_packed", "wfl_run_resident", "wfl_download_results", "wfl_get_stats", "wfl_set_option",
+           "wfl_pack_results", "wfl_packed_results_layout", "wfl_debug_gene_scores", "wfl_host_alloc",
+           "wfl_host_free"]
+ABI_VERSION = 2
+PACKED_MAX_NODES, PACKED_MAX_COORD, PACKED_MAX_SYSTEMS = 16384, 65535, 8
 
 
 class CBatch(ctypes.Structure):
@@ -34,6 +38,15 @@ class CBatch(ctypes.Structure):
                 ("hit_qstart", c_i32p), ("hit_qend", c_i32p), ("hit_taxon", c_i32p),
                 ("hit_score", c_f64p), ("hit_scov", c_f64p), ("hit_strand", c_i8p),
                 ("hit_sysmask", c_u32p),
+                ("locus_start", c_i32p), ("locus_end", c_i32p), ("locus_strand", c_i8p)]
+
+
+class CPackedBatch(ctypes.Structure):
+    """`wfl_packed_batch` (compact wire format, 14 B/hit)."""
+    _fields_ = [("n_contigs", ctypes.c_int64), ("n_hits", ctypes.c_int64), ("n_loci", ctypes.c_int64),
+                ("hit_off", c_i64p), ("locus_off", c_i64p),
+                ("hit_qstart16", c_u16p), ("hit_qend16", c_u16p), ("hit_tax16", c_u16p),
+                ("hit_score", c_f64p), ("hit_sysmask8", c_u8p),
                 ("locus_start", c_i32p), ("locus_end", c_i32p), ("locus_strand", c_i8p)]
 
 
@@ -52,7 +65,8 @@ class CStats(ctypes.Structure):
     """`wfl_stats`."""
     _fields_ = [(k, ctypes.c_int64) for k in
                 ("kernel_launches", "contigs", "hits", "loci", "matched_pairs", "groups", "levels",
-                 "pairs_tested", "pairs_scored", "workspace_retries", "smem_contigs")] + \
+                 "pairs_tested", "pairs_scored", "workspace_retries", "smem_contigs", "fallback_contigs",
+                 "guard_trips", "refined_groups", "host_syncs")] + \
                [("phase_cycles", ctypes.c_int64 * 12)] + \
                [(k, ctypes.c_float) for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_score_kernel")]
 
@@ -85,11 +99,18 @@ def load_library(path=None):
     lib.wfl_set_taxonomy.argtypes = [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_i32p, c_i32p, c_u8p,
                                      ctypes.c_int32, ctypes.c_int32]
     lib.wfl_score_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(CBatch), ctypes.POINTER(CResults)]
+    lib.wfl_score_packed.argtypes = [ctypes.c_void_p, ctypes.POINTER(CPackedBatch), ctypes.POINTER(CResults)]
     lib.wfl_upload_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(CBatch)]
+    lib.wfl_upload_packed.argtypes = [ctypes.c_void_p, ctypes.POINTER(CPackedBatch)]
     lib.wfl_run_resident.argtypes = [ctypes.c_void_p]
     lib.wfl_download_results.argtypes = [ctypes.c_void_p, ctypes.POINTER(CResults)]
     lib.wfl_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(CStats)]
-    lib.wfl_configure.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.wfl_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
+    lib.wfl_pack_results.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                     ctypes.POINTER(ctypes.c_void_p)]
+    lib.wfl_packed_results_layout.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                              ctypes.POINTER(ctypes.c_int64 * 18)]
+    lib.wfl_packed_results_layout.restype = ctypes.c_int64
     lib.wfl_debug_gene_scores.argtypes = [ctypes.c_void_p, ctypes.c_int64, c_i32p, c_i32p, c_f64p,
                                           ctypes.c_int64]
     lib.wfl_debug_gene_scores.restype = ctypes.c_int64
@@ -145,7 +166,7 @@ class Engine:
 
     def __init__(self, device=0, params=None, taxonomy=None):
         self._lib = load_library()
-        if self._lib.wfl_abi_version() != 1:
+        if self._lib.wfl_abi_version() != ABI_VERSION:
             raise EngineError("ABI version mismatch")
         h = ctypes.c_void_p()
         rc = self._lib.wfl_create(int(device), ctypes.byref(h))
@@ -193,8 +214,9 @@ class Engine:
                 rc, self._lib.wfl_last_error(self._h).decode()))
 
     # ------------------------------------------------------------------
-    def configure(self, threads=0, smem_bytes=0, ctas_per_sm=0):
-        self._check(self._lib.wfl_configure(self._h, threads, smem_bytes, ctas_per_sm))
+    def set_option(self, name, value):
+        """Tuning / test knobs by name (include/waafle_b200.h: wfl_set_option), e.g. exact=1."""
+        self._check(self._lib.wfl_set_option(self._h, name.encode(), int(value)))
 
     def set_params(self, params):
         if isinstance(params, dict):
@@ -215,25 +237,32 @@ class Engine:
 
     # ------------------------------------------------------------------
     def _cbatch(self, batch):
+        """ctypes view of a batch in either wire format; returns (struct, n, nh, nl, packed)."""
         a = batch.arrays() if hasattr(batch, "arrays") else batch
-        k = dict(
-            hit_off=_as(a["hit_off"], np.int64), locus_off=_as(a["locus_off"], np.int64),
-            hit_qstart=_as(a["hit_qstart"], np.int32), hit_qend=_as(a["hit_qend"], np.int32),
-            hit_taxon=_as(a["hit_taxon"], np.int32), hit_score=_as(a["hit_score"], np.float64),
-            hit_scov=_as(a["hit_scov"], np.float64), hit_strand=_as(a["hit_strand"], np.int8),
-            locus_start=_as(a["locus_start"], np.int32), locus_end=_as(a["locus_end"], np.int32),
-            locus_strand=_as(a["locus_strand"], np.int8))
-        n, nh, nl = len(k["hit_off"]) - 1, len(k["hit_qstart"]), len(k["locus_start"])
-        cb = CBatch(n_contigs=n, n_hits=nh, n_loci=nl)
+        packed = "hit_tax16" in a
+        if packed:
+            spec = dict(hit_off=np.int64, locus_off=np.int64, hit_qstart16=np.uint16, hit_qend16=np.uint16,
+                        hit_tax16=np.uint16, hit_score=np.float64, locus_start=np.int32, locus_end=np.int32,
+                        locus_strand=np.int8)
+            mask_name, mask_dtype, cls = "hit_sysmask8", np.uint8, CPackedBatch
+        else:
+            spec = dict(hit_off=np.int64, locus_off=np.int64, hit_qstart=np.int32, hit_qend=np.int32,
+                        hit_taxon=np.int32, hit_score=np.float64, hit_scov=np.float64, hit_strand=np.int8,
+                        locus_start=np.int32, locus_end=np.int32, locus_strand=np.int8)
+            mask_name, mask_dtype, cls = "hit_sysmask", np.uint32, CBatch
+        k = {name: _as(a[name], dt) for name, dt in spec.items()}
+        n, nh, nl = len(k["hit_off"]) - 1, len(k["hit_score"]), len(k["locus_start"])
+        cb = cls(n_contigs=n, n_hits=nh, n_loci=nl)
+        ftypes = dict(cls._fields_)
         for name, arr in k.items():
-            setattr(cb, name, _ptr(arr, dict(CBatch._fields_)[name]._type_))
+            setattr(cb, name, _ptr(arr, ftypes[name]._type_))
         if self.n_systems > 0:
-            if a.get("hit_sysmask") is None:
-                raise EngineError("params.n_systems > 0 but the batch has no hit_sysmask")
-            k["hit_sysmask"] = _as(a["hit_sysmask"], np.uint32)
-            cb.hit_sysmask = _ptr(k["hit_sysmask"], ctypes.c_uint32)
+            if a.get(mask_name) is None:
+                raise EngineError("params.n_systems > 0 but the batch has no " + mask_name)
+            k[mask_name] = _as(a[mask_name], mask_dtype)
+            setattr(cb, mask_name, _ptr(k[mask_name], ftypes[mask_name]._type_))
         self._keep = k   # keep the arrays alive while the C side reads them
-        return cb, n, nh, nl
+        return cb, n, nh, nl, packed
 
     def _alloc_results(self, n, nl, members_capacity):
         S = self.n_systems
@@ -274,11 +303,12 @@ class Engine:
 
     def score_batch(self, batch):
         """Host arrays in, host arrays out (H2D + kernels + D2H inside the call)."""
-        cb, n, nh, nl = self._cbatch(batch)
+        cb, n, nh, nl, packed = self._cbatch(batch)
+        call = self._lib.wfl_score_packed if packed else self._lib.wfl_score_batch
         cap = max(4 * n, 1024)
         for _ in range(2):
             r, cr = self._alloc_results(n, nl, cap)
-            rc = self._lib.wfl_score_batch(self._h, ctypes.byref(cb), ctypes.byref(cr))
+            rc = call(self._h, ctypes.byref(cb), ctypes.byref(cr))
             if rc == -4:   # WFL_ERR_CAPACITY: results are resident, fetch with a larger buffer
                 cap = int(cr.members_used)
                 r, cr = self._alloc_results(n, nl, cap)
@@ -287,8 +317,9 @@ class Engine:
             return self._finish(r, cr)
 
     def upload(self, batch):
-        cb, n, nh, nl = self._cbatch(batch)
-        self._check(self._lib.wfl_upload_batch(self._h, ctypes.byref(cb)))
+        cb, n, nh, nl, packed = self._cbatch(batch)
+        call = self._lib.wfl_upload_packed if packed else self._lib.wfl_upload_batch
+        self._check(call(self._h, ctypes.byref(cb)))
         self._resident = (n, nl)
 
     def run_resident(self):
@@ -303,6 +334,19 @@ class Engine:
             rc = self._lib.wfl_download_results(self._h, ctypes.byref(cr))
         self._check(rc)
         return self._finish(r, cr)
+
+    def score_batch_device(self, batch):
+        """Plugin call that leaves the results on the device (multi-GPU: they are gathered with NCCL from there)."""
+        cb, n, nh, nl, packed = self._cbatch(batch)
+        call = self._lib.wfl_score_packed if packed else self._lib.wfl_score_batch
+        self._check(call(self._h, ctypes.byref(cb), None))
+        self._resident = (n, nl)
+
+    def pack_results(self):
+        """The compacted results of the last run as ONE device buffer: (device pointer, bytes, cudaStream_t)."""
+        p, nb, st = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p()
+        self._check(self._lib.wfl_pack_results(self._h, ctypes.byref(p), ctypes.byref(nb), ctypes.byref(st)))
+        return p.value, nb.value, st.value
 
     def stats(self):
         s = CStats()
@@ -323,3 +367,33 @@ class Engine:
         if m > capacity:
             return self.debug_gene_scores(contig, int(m))
         return cl[:m], lo[:m], sc[:m]
+
+
+_SECTIONS = [("call", np.uint8), ("direction", np.uint8), ("lifts", np.int32), ("clade1", np.int32),
+             ("clade2", np.int32), ("lca", np.int32), ("best1", np.int32), ("best2", np.int32),
+             ("crit", np.float64), ("rank", np.float64), ("member_off", np.int64), ("n_members_a", np.int32),
+             ("members", np.int32), ("synteny", np.uint8), ("locus_flags", np.uint8), ("ann_winner", np.int32),
+             ("call_counts", np.int64), ("call_index", np.int64)]
+
+
+def results_layout(n, nl, S, members):
+    """Byte offsets of the 18 sections of a packed results buffer and its total size (wfl_packed_results_layout)."""
+    off = (ctypes.c_int64 * 18)()
+    total = load_library().wfl_packed_results_layout(n, nl, S, members, ctypes.byref(off))
+    return list(off), int(total)
+
+
+def unpack_results(blob):
+    """Host copy of a packed results buffer (uint8 array) -> the dict Engine.score_batch returns."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    n, nl, S, members = (int(x) for x in blob[:32].view(np.int64))
+    off, total = results_layout(n, nl, S, members)
+    counts = dict(call=n, direction=n, lifts=n, clade1=n, clade2=n, lca=n, best1=n, best2=n, crit=n, rank=n,
+                  member_off=n + 1, n_members_a=n, members=members, synteny=nl, locus_flags=nl,
+                  ann_winner=nl * S, call_counts=3, call_index=n)
+    out = {}
+    for (name, dt), o in zip(_SECTIONS, off):
+        cnt = counts[name]
+        out[name] = blob[o:o + cnt * np.dtype(dt).itemsize].view(dt).copy()
+    out["ann_winner"] = out["ann_winner"].reshape(nl, S)
+    return out

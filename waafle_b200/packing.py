@@ -70,6 +70,26 @@ class Batch:
             contig_lengths=cut(self.contig_lengths, c0, c1),
             hit_row=cut(self.hit_row, h0, h1), locus_row=cut(self.locus_row, l0, l1))
 
+    def can_pack(self, n_nodes, n_systems=0):
+        """True if the compact wire format (wfl_packed_batch) can carry this batch."""
+        hi = max(int(self.hit_qstart.max(initial=0)), int(self.hit_qend.max(initial=0)))
+        lo = min(int(self.hit_qstart.min(initial=0)), int(self.hit_qend.min(initial=0)))
+        return n_nodes <= 16384 and n_systems <= 8 and lo >= 0 and hi <= 65535
+
+    def to_packed(self, min_scov):
+        """The device-facing arrays in the compact wire format (14 B/hit instead of 29): the scov filter of
+        waafle_orgscorer.py:362 is applied here (one bit), the strand is one bit, taxon and coordinates 16-bit."""
+        tax16 = (self.hit_taxon.astype(np.uint16)
+                 | np.where(self.hit_strand == ord("-"), np.uint16(0x4000), np.uint16(0))
+                 | np.where(self.hit_scov >= min_scov, np.uint16(0x8000), np.uint16(0))).astype(np.uint16)
+        out = dict(hit_off=self.hit_off, locus_off=self.locus_off,
+                   hit_qstart16=self.hit_qstart.astype(np.uint16), hit_qend16=self.hit_qend.astype(np.uint16),
+                   hit_tax16=tax16, hit_score=self.hit_score, locus_start=self.locus_start,
+                   locus_end=self.locus_end, locus_strand=self.locus_strand)
+        if self.hit_sysmask is not None:
+            out["hit_sysmask8"] = self.hit_sysmask.astype(np.uint8)
+        return out
+
     def algorithmic_bytes(self, n_systems=0):
         """29 B/hit + 9 B/locus + 16 B/contig in, 40 + G(1+4S) B/contig out."""
         return (29 * self.n_hits + 9 * self.n_loci + 16 * self.n_contigs

@@ -102,26 +102,27 @@ class Synth:
             contig_names=[self.contig_name(i) for i in range(self.n_contigs)],
             contig_lengths=self.contig_len.astype(np.int64))
 
-    def write_files(self, outdir, stem="synth"):
-        """Write <stem>.fna/.blastout/.gff/.taxonomy.tsv for the reference CLI / front end."""
+    def write_files(self, outdir, stem="synth", c0=0, c1=None):
+        """Write <stem>.fna/.blastout/.gff/.taxonomy.tsv for the reference CLI / front end (contigs [c0, c1))."""
         os.makedirs(outdir, exist_ok=True)
+        c1 = self.n_contigs if c1 is None else c1
         p = lambda ext: os.path.join(outdir, stem + ext)
         with open(p(".taxonomy.tsv"), "w") as fh:
             for nm, par in zip(self.tax_names, self.tax_parent):
                 fh.write("{}\t{}\n".format(nm, "r__Root" if par < 0 else self.tax_names[par]))
         with open(p(".fna"), "w") as fh:
-            for i, ln in enumerate(self.contig_len):
+            for i in range(c0, c1):
                 fh.write(">{} synthetic\n".format(self.contig_name(i)))
-                fh.write("N" * int(ln) + "\n")
+                fh.write("N" * int(self.contig_len[i]) + "\n")
         with open(p(".gff"), "w") as fh:
             fh.write("##gff-version  3\n")
-            for i in range(self.n_contigs):
+            for i in range(c0, c1):
                 for g in range(self.gene_off[i], self.gene_off[i + 1]):
                     fh.write("{}\tsynth\tCDS\t{}\t{}\t.\t{}\t0\tID={}_{}\n".format(
                         self.contig_name(i), self.gene_start[g], self.gene_end[g],
                         chr(self.gene_strand[g]), i, g))
         with open(p(".blastout"), "w") as fh:
-            for i in range(self.n_contigs):
+            for i in range(c0, c1):
                 for h in range(self.hit_off[i], self.hit_off[i + 1]):
                     sp = int(self.hit_species[h])
                     tname = (self.tax_names[self.species_node[sp]] if sp >= 0
