@@ -158,6 +158,9 @@ typedef struct {
     int64_t workspace_retries;  /* contigs replayed by the exact pipeline with a larger workspace */
     int64_t smem_contigs;       /* contigs scored entirely in shared memory by the fused fast-path kernel */
     int64_t fallback_contigs;   /* contigs the fast path handed to the exact pipeline (capacity or guard band) */
+    int64_t second_pass_contigs;/* contigs the first fast pass handed to the second one (larger shared-memory slice) */
+    int64_t fallback_reasons[8];/* hand-overs of both passes by cause: loci, hits, coordinates, records, clades,
+                                   groups, pairs, guard band */
     int64_t guard_trips;        /* ... of which because a rank comparison fell inside the 1e-12 guard band */
     int64_t refined_groups;     /* gene scores recomputed in numpy's summation order inside the fast kernel */
     int64_t host_syncs;         /* stream synchronisations inside the last call          */
@@ -210,6 +213,28 @@ int  wfl_pack_results(wfl_engine *e, void **dev_ptr, int64_t *bytes, void **stre
  * n_members_a, members, synteny, locus_flags, ann_winner, call_counts, call_index} and the total size */
 int64_t wfl_packed_results_layout(int64_t n_contigs, int64_t n_loci, int32_t n_systems, int64_t n_members,
                                   int64_t offsets[18]);
+
+/* ---- front end on the device: BLAST outfmt-6 text -> hit columns -------------------------------
+ * Replaces the per-row Hit objects of waafle/utils.py:192-241 / iter_contig_hits :255-270.  The caller ships the raw
+ * text of a blastout file; the device splits rows and fields, converts the numbers exactly, computes scov_modified and
+ * waafle_score in the reference's operation order (utils.py:214-229), dictionary-codes the taxon (sseqid field 1) and
+ * the annotation systems (fields 2+) against hash sets of the file's DISTINCT names, and flags contig block starts.
+ * Rows it cannot reproduce exactly are counted in *flagged: the caller must then use its CPU reader. */
+typedef struct wfl_parser wfl_parser;
+int  wfl_parser_create(int device, wfl_parser **out);
+void wfl_parser_destroy(wfl_parser *p);
+const char *wfl_parser_last_error(const wfl_parser *p);
+/* returns the number of rows or a negative wfl_status */
+int64_t wfl_parse_blast(wfl_parser *p, const char *text, int64_t n_bytes, int32_t *flagged, int64_t *first_flagged);
+/* distinct-name sets of the last parse: kind 0 = taxa (2^20 slots), 1 = annotation systems (64 slots); hash[s] != 0 marks
+ * an occupied slot and (off[s], len[s]) is one occurrence of its name in the text */
+int  wfl_parse_distinct(wfl_parser *p, int kind, uint64_t *hash, int64_t *off, int32_t *len, int32_t slots);
+/* sys_perm[slot] = bit of that system in the sorted system list (-1 for empty slots); columns of [n_rows] each, NULL = skip;
+ * tcode[r] = slot of the row's taxon in the distinct-taxon set; newblock[r] = qseqid differs from the previous row's */
+int  wfl_parse_fetch(wfl_parser *p, const int32_t *sys_perm, int32_t *qstart, int32_t *qend, double *score, double *scov,
+                     int8_t *strand, int32_t *tcode, uint32_t *sysmask, int64_t *ss_off, int32_t *ss_len, uint8_t *newblock,
+                     int64_t *q_off, int32_t *q_len);
+int  wfl_parser_times(const wfl_parser *p, float *ms_h2d, float *ms_kernels, float *ms_d2h);
 
 /* Page-locked host memory for callers without a CUDA binding of their own (pinned buffers make the
  * H2D / D2H copies of wfl_score_batch asynchronous and ~2x faster).  Free with wfl_host_free. */

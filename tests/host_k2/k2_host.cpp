@@ -97,8 +97,8 @@ int main(int argc, char **argv) {
             }
         }
     }
-    // the fast path's closed-form integral (group_integral: descending-score picks with a connected union, generic
-    // endpoint sweep when a pick leaves a gap) against the literal site array, within 1e-13 relative
+    // the fast path's closed-form integral (group_integral: records in descending score order, connected union, generic
+    // endpoint sweep when a record leaves a gap) against the literal site array, within 1e-13 relative
     long fbad = 0, fdone = 0;
     for (int it = 0; it < cases; ++it) {
         const int n = 50 + rng() % 3000;
@@ -120,14 +120,15 @@ int main(int argc, char **argv) {
             bv[i] = v;
             bord[i] = (u16)i;
         }
-        std::shuffle(bord.begin(), bord.end(), rng);
+        // descending score order, ties in buffer order: what the fast path's per-locus sort delivers
+        std::stable_sort(bord.begin(), bord.end(), [&](u16 x, u16 y) { return bv[x] > bv[y]; });
         std::vector<double> site(n, 0.0);
         for (int i = 0; i < k; ++i)
             for (int p = (int)(bab[i] & 0xffffu); p < (int)(bab[i] >> 16); ++p) site[p] = std::max(site[p], bv[i]);
         const double want = pw(site.data(), n);
         for (int general = 0; general < 2; ++general) {
             const double got = general ? group_integral_general(bv.data(), bab.data(), bord.data(), 0, k)
-                                       : group_integral(bv.data(), bab.data(), bord.data(), 0, k);
+                                       : group_integral(bv.data(), bab.data(), bord.data(), 0, k, n);
             ++fdone;
             if (std::fabs(got - want) > 1e-13 * std::max(1.0, std::fabs(want))) {
                 if (++fbad <= 10) fprintf(stderr, "FAST MISMATCH case %d n=%d k=%d general=%d got %a want %a\n", it, n, k, general, got, want);

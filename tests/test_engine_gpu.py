@@ -234,6 +234,29 @@ def test_full_size_bit_exact_vs_c_oracle(engine, config, n, flags):
         assert not helpers.compare_results(ref, got, score_rtol=SCORE_RTOL), "packed"
 
 
+@pytest.mark.parametrize("config,n,flags", [
+    ("cfg2", 30000, {}),
+    ("cfg3", 20000, dict(weak_loci="penalize", range=0.2)),
+    ("cfg5", 20000, dict(weak_loci="assign-unknown")),
+])
+def test_presorted_hits_bit_exact_vs_c_oracle(engine, config, n, flags):
+    """What the front end's packer delivers: every contig's hits in descending score order (Batch.sort_hits).  The fast
+    kernel then skips its per-locus sort; results -- annotation winners included -- equal the C restatement's on the
+    same batch, and (but for the hit indices) the unsorted batch's."""
+    from waafle_b200 import synth
+    data = synth.generate_config(config, n_contigs=n, seed=1001, annotations=(config == "cfg5"))
+    tax = data.taxonomy()
+    raw = data.to_batch(tax)
+    batch = raw.sort_hits()
+    P = helpers.params_for(flags, 1 if config == "cfg5" else 0)
+    ref = c_oracle.score_batch(P, tax, batch)
+    check_vs_ref(engine, P, tax, batch, ref, (config, flags, "sorted"))
+    got = run_engine(engine, P, tax, batch)
+    unsorted = run_engine(engine, P, tax, raw)
+    for k in ("call", "clade1", "clade2", "lca", "lifts", "synteny", "locus_flags", "members", "crit", "rank"):
+        assert np.array_equal(got[k], unsorted[k]), k
+
+
 def test_fast_path_capacity_fallbacks():
     """Tiny slice capacities: most contigs overflow the fast kernel's shared-memory slice and are handed to the exact
     pipeline; results do not change (calls bit-exact, scores within tolerance)."""

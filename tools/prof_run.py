@@ -23,7 +23,7 @@ def main():
     opts = [x.split("=") for x in a[3:]]
     data = synth.generate_config(workload, n_contigs=n, seed=1000)
     tax = data.taxonomy()
-    batch = data.to_batch(tax)
+    batch = data.to_batch(tax).sort_hits()
     P = OrgscorerParams(n_systems=1 if batch.hit_sysmask is not None else 0)
     eng = Engine(0, P, tax)
     for k, v in opts:

@@ -43,7 +43,8 @@ struct wfl_engine {
     bool packed = false;                 // the resident batch is in the compact wire format
     // options (wfl_set_option / environment)
     bool exact = false;                  // every contig through the exact pipeline
-    int fast_kcap = 0, fast_tcap = 0, fast_ncap = 0;
+    int fast_kcap = 0, fast_mcap = 0, fast_tcap = 0, fast_ncap = 0;
+    int fast_passes = 2;                 // 1: no second pass with a larger slice
     size_t pipe_pool_bytes = size_t(8192) << 20;
     size_t k2_cap_override = 0;
     bool chunk_fixed = false;
@@ -52,8 +53,9 @@ struct wfl_engine {
     Buf fb_list, fast_scratch, fast_wq, blob, status_tmp;
     int plan_nmax = 0;
     int tax_max_depth = 0, anc_rows = 0;
-    FastCfg fcfg{};
-    int fast_grid = 0;
+    FastCfg fcfg{}, fcfg2{};            // first pass (all contigs) / second pass (capacity overflows, larger slice)
+    int fast_grid = 0, fast_grid2 = 0;
+    int64_t cfg_key[4] = {-1, -1, -1, -1};
     // exact pipeline state
     Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2], k2_desc[2], k2_order[2], k2_keys[2], k2_meta[2];
     std::vector<int64_t> h_hit_off, h_locus_off;
@@ -508,37 +510,64 @@ int run_pipeline_list(wfl_engine *e, DevCounters *ctr, const std::vector<int> &l
     return WFL_OK;
 }
 
-// Capacities of the fast kernel's shared-memory slice, chosen from the shape of the batch (options override).
-void choose_fast_cfg(wfl_engine *e) {
-    const double hbar = e->n > 0 ? (double)e->nh / (double)e->n : 0.0;        // hits per contig
-    const double kbar = e->nl > 0 ? (double)e->nh / (double)e->nl : 0.0;      // hits per locus
-    auto r32 = [](double x) { return (int)((x + 31.0) / 32.0) * 32; };
-    int K = e->fast_kcap ? e->fast_kcap : std::min(1024, std::max(64, r32(1.8 * kbar + 24)));
-    int T = e->fast_tcap ? e->fast_tcap : std::min(2048, std::max(64, r32(0.6 * hbar + 40)));
-    int N = e->fast_ncap ? e->fast_ncap : std::min(8192, std::max(96, r32(0.9 * hbar + 48)));
-    K = (K + 1) & ~1;
-    int C = 64;
-    while (C * 3 < T * 4) C <<= 1;   // load factor <= 0.75
+// Capacities of the fast kernel's shared-memory slices, chosen from the shape of the batch (options override).
+// First pass: sized for the bulk of the contigs (hits per contig up to ~1.6x the mean), so that as many warps as possible
+// are resident; second pass: the contigs that overflowed, with a slice ~3x as large.
+static void fit_layout(wfl_engine *e, FastCfg &F, int K, int M, int T, int N, int Sc) {
     for (;;) {
-        fast_layout(e->fcfg, K, C, T, N, e->S > 0);
-        if ((size_t)fast_warps_per_cta() * e->fcfg.slice_bytes + 1024 <= e->smem_optin) break;
+        int C = 64;
+        while (C * 3 < T * 4) C <<= 1;   // load factor <= 0.75
+        fast_layout(F, K, M, C, T, N, Sc);
+        if ((size_t)fast_warps_per_cta() * F.slice_bytes + 1024 <= e->smem_optin) break;
         // does not fit one CTA: shrink the largest consumers
-        if (N > 96) N = std::max(96, N / 2);
-        else if (T > 64) { T = std::max(64, T / 2); C = std::max(64, C / 2); }
-        else if (K > 64) K = std::max(64, K / 2);
-        else break;
+        if (N > 96) N = std::max(96, N * 3 / 4);
+        if (T > 64) T = std::max(64, T * 3 / 4);
+        if (M > 128) M = std::max(128, M * 3 / 4);
+        if (K > 64) K = std::max(64, K * 3 / 4);
+        if (Sc > 64) Sc = std::max(64, Sc / 2);
+        if (N <= 96 && T <= 64 && M <= 128 && K <= 64) break;
     }
-    const int cpsm = std::max(1, fast_ctas_per_sm(e->fcfg, e->packed, 0));
-    e->fast_grid = e->sm_count * cpsm;
 }
 
-int launch_fast_range(wfl_engine *e, DevCounters *ctr, int64_t c0, int64_t n_work, int launch_idx, cudaStream_t stream) {
+void choose_fast_cfg(wfl_engine *e) {
+    int64_t hmax = 0;
+    for (int64_t c = 0; c < e->n; ++c) hmax = std::max(hmax, e->h_hit_off[c + 1] - e->h_hit_off[c]);
+    const int64_t key[4] = {e->nh, e->nl, e->n * 2 + (e->packed ? 1 : 0), hmax};
+    if (!memcmp(key, e->cfg_key, sizeof key)) return;
+    const double hbar = e->n > 0 ? (double)e->nh / (double)e->n : 0.0;        // hits per contig
+    const double kbar = e->nl > 0 ? (double)e->nh / (double)e->nl : 0.0;      // hits per locus
+    auto r16 = [](double x) { return (int)((x + 15.0) / 16.0) * 16; };
+    const double hq = std::min((double)hmax, 1.6 * hbar);
+    const int K = e->fast_kcap ? e->fast_kcap : std::min(2048, std::max(64, r16(1.8 * kbar + 24)));
+    const int M = e->fast_mcap ? e->fast_mcap : std::min(16384, std::max(128, r16(hq + 16)));
+    const int T = e->fast_tcap ? e->fast_tcap : std::min(4096, std::max(64, r16(0.42 * hq + 16)));
+    const int N = e->fast_ncap ? e->fast_ncap : std::min(16384, std::max(96, r16(0.6 * hq + 32)));
+    fit_layout(e, e->fcfg, (K + 1) & ~1, M, T, N, 64);
+    fit_layout(e, e->fcfg2, (3 * K + 1) & ~1, 3 * M, 3 * T, 3 * N, 2048);
+    e->fast_grid = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfg, e->packed, 0));
+    e->fast_grid2 = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfg2, e->packed, 0));
+    memcpy(e->cfg_key, key, sizeof key);
+}
+
+// One launch of the fused fast-path kernel: pass 0 over the contig range [c0, c0 + n_work), pass 1 over the first
+// pass's capacity overflows (list and count on the device).
+int launch_fast_pass(wfl_engine *e, DevCounters *ctr, int pass, int64_t c0, int64_t n_work, int launch_idx, cudaStream_t stream) {
     FastArgs a{};
     a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
-    a.cfg = e->fcfg;
+    a.cfg = pass ? e->fcfg2 : e->fcfg;
     a.wq = static_cast<unsigned long long *>(e->fast_wq.p) + launch_idx;
-    a.n_work = n_work; a.work_base = c0; a.work_list = nullptr;
-    a.fb_list = static_cast<int *>(e->fb_list.p);
+    int *fb_a = static_cast<int *>(e->fb_list.p), *fb_b = fb_a + e->n + 1;
+    a.fb_final = fb_b;
+    a.fb_final_count = &ctr->n_fallback2;
+    if (pass == 0) {
+        a.n_work = n_work; a.work_base = c0; a.work_list = nullptr; a.n_work_dev = nullptr;
+        a.fb_list = e->fast_passes > 1 ? fb_a : fb_b;
+        a.fb_count = e->fast_passes > 1 ? &ctr->n_fallback : &ctr->n_fallback2;
+    } else {
+        a.n_work = 0; a.work_base = 0; a.work_list = fb_a; a.n_work_dev = &ctr->n_fallback;
+        a.fb_list = fb_b;
+        a.fb_count = &ctr->n_fallback2;
+    }
     a.anc = static_cast<const int *>(e->anc.p);
     a.anc_rows = e->anc_rows;
     a.guard = 1e-12;
@@ -547,7 +576,7 @@ int launch_fast_range(wfl_engine *e, DevCounters *ctr, int64_t c0, int64_t n_wor
     a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
     a.scratch = static_cast<char *>(e->fast_scratch.p);
     const int wpc = fast_warps_per_cta();
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(e->fast_grid, (n_work + wpc - 1) / wpc));
+    const int grid = pass ? e->fast_grid2 : (int)std::max<int64_t>(1, std::min<int64_t>(e->fast_grid, (n_work + wpc - 1) / wpc));
     cudaError_t err = launch_fast(a, e->packed, grid, stream);
     if (err != cudaSuccess) { set_err(e, "fast kernel launch failed: %s", cudaGetErrorString(err)); return WFL_ERR_CUDA; }
     e->stats.kernel_launches++;
@@ -618,9 +647,9 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
     if (use_fast) {
         choose_fast_cfg(e);
         char *fs;
-        if ((rc = outbuf(e, e->fb_list, (size_t)e->n + 1, &fb_list))) return rc;
+        if ((rc = outbuf(e, e->fb_list, 2 * ((size_t)e->n + 1), &fb_list))) return rc;
         if ((rc = outbuf(e, e->fast_wq, 256, &fwq))) return rc;
-        if ((rc = outbuf(e, e->fast_scratch, (size_t)e->fast_grid * fast_warps_per_cta() * e->fcfg.Kcap * 16, &fs))) return rc;
+        if ((rc = outbuf(e, e->fast_scratch, (size_t)std::max(e->fast_grid, e->fast_grid2) * fast_warps_per_cta() * e->fcfg2.Kcap * 16, &fs))) return rc;
         CU(cudaMemsetAsync(fwq, 0, 256 * sizeof(unsigned long long), e->stream));
     }
     CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
@@ -644,7 +673,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
             if (streamed && e->chunks_streamed) CU(cudaStreamWaitEvent(st, e->chunk_ev[k], 0));
             if (use_fast) {
                 if (k >= 250) { set_err(e, "too many chunks"); return WFL_ERR_ARG; }
-                if ((rc = launch_fast_range(e, ctr, c0, c1 - c0, (int)k, st))) return rc;
+                if ((rc = launch_fast_pass(e, ctr, 0, c0, c1 - c0, (int)k, st))) return rc;
             } else {
                 if ((rc = launch_pipeline(e, ctr, nullptr, c0, c1 - c0, (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]), slot, 1))) return rc;
             }
@@ -653,6 +682,9 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
             CU(cudaEventRecord(e->ev_join, e->stream2));
             CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
         }
+        // second pass: the contigs that overflowed a capacity of the first pass's slice, with a larger slice (their list
+        // and count are on the device: no host round trip)
+        if (use_fast && e->fast_passes > 1 && (rc = launch_fast_pass(e, ctr, 1, 0, 0, 255, e->stream))) return rc;
     }
     CU(cudaEventRecord(e->ev[2], e->stream));
     trace("kernels launched");
@@ -708,9 +740,13 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         }
         // contigs for the exact pipeline: fast-path fallbacks (first round) and workspace overflows (status 1)
         std::vector<int> list;
-        if (attempt == 0 && hc.n_fallback) {
-            list.resize((size_t)hc.n_fallback);
-            CU(cudaMemcpy(list.data(), fb_list, list.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        if (attempt == 0 && use_fast) {
+            e->stats.second_pass_contigs = e->fast_passes > 1 ? (int64_t)hc.n_fallback : 0;
+            for (int q = 0; q < 8; ++q) e->stats.fallback_reasons[q] = (int64_t)hc.fb_reason[q];
+        }
+        if (attempt == 0 && hc.n_fallback2) {
+            list.resize((size_t)hc.n_fallback2);
+            CU(cudaMemcpy(list.data(), fb_list + e->n + 1, list.size() * sizeof(int), cudaMemcpyDeviceToHost));
             std::sort(list.begin(), list.end());
             e->stats.fallback_contigs = (int64_t)list.size();
         } else if (hc.n_overflow) {
@@ -725,7 +761,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         if (attempt > 8) { set_err(e, "workspace keeps overflowing"); return WFL_ERR_CUDA; }
         unsigned long long zero = 0;
         CU(cudaMemcpyAsync(&ctr->n_overflow, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
-        CU(cudaMemcpyAsync(&ctr->n_fallback, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(&ctr->n_fallback2, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
         if ((rc = run_pipeline_list(e, ctr, list, grow))) return rc;
     }
     e->members_total = totals[0];
@@ -948,7 +984,9 @@ int wfl_set_option(wfl_engine *e, const char *name, int64_t value) {
     const std::string k(name);
     if (k == "exact") e->exact = value != 0;
     else if (k == "fast_kcap") e->fast_kcap = (int)std::max<int64_t>(0, value);
+    else if (k == "fast_mcap") e->fast_mcap = (int)std::max<int64_t>(0, value);
     else if (k == "fast_tcap") e->fast_tcap = (int)std::max<int64_t>(0, value);
+    else if (k == "fast_passes") e->fast_passes = value >= 2 ? 2 : 1;
     else if (k == "fast_ncap") e->fast_ncap = (int)std::max<int64_t>(0, value);
     else if (k == "pool_mb") e->pipe_pool_bytes = (size_t)std::max<int64_t>(0, value) << 20;
     else if (k == "chunk_mb") { e->chunk_bytes = (size_t)std::max<int64_t>(1, value) << 20; e->chunk_fixed = true; }
@@ -956,6 +994,7 @@ int wfl_set_option(wfl_engine *e, const char *name, int64_t value) {
     else if (k == "k2_cap") e->k2_cap_override = (size_t)std::max<int64_t>(0, value);
     else { set_err(e, "unknown option %s", name); return WFL_ERR_ARG; }
     e->have_results = false;
+    e->cfg_key[0] = -1;
     return WFL_OK;
 }
 

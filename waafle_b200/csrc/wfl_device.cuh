@@ -57,7 +57,9 @@ struct DevCounters {
     unsigned long long n_runaway;
     unsigned long long n_badinput;      // contigs with a taxon index outside the taxonomy
     unsigned long long matched_pairs, groups, levels, pairs_tested, pairs_scored, smem_contigs;
-    unsigned long long n_fallback;      // contigs the fused fast-path kernel handed to the exact pipeline
+    unsigned long long n_fallback;      // contigs the first fast-path pass handed on (to the second pass)
+    unsigned long long n_fallback2;     // contigs the second pass (larger slice) handed to the exact pipeline
+    unsigned long long fb_reason[8];    // why (both passes): loci, hits, coordinates, records, clades, groups, pairs, guard
     unsigned long long guard_trips;     // ... of which because a rank comparison fell inside the guard band
     unsigned long long refined_groups;  // gene scores recomputed exactly inside the fast kernel (near a threshold)
     unsigned long long phase_cycles[12];   // thread-0 clock64 deltas per phase (profiling aid)
@@ -81,14 +83,17 @@ struct PlanEntry {
 // Layout of one warp's shared-memory slice (byte offsets) and its capacities; computed on the host.
 struct FastCfg {
     int slice_bytes;
+    int Hcap;      // hits of one contig (staging of the spans)
+    int Mcap;      // records (hit x locus matches) of one contig
     int Kcap;      // records of one locus
     int cmask;     // clade hash slots - 1 (power of two)
     int Tcap;      // distinct clades per level
     int Ncap;      // (clade, locus) groups per level
     int Scap;      // two-clade pairs that pass the mask prefilter
-    int o_llo, o_llen, o_lraw, o_lstr, o_goff, o_maxv, o_unk;
-    int o_bv, o_bab, o_bt, o_bcl, o_bh;
-    int o_hkey, o_hval, o_clid, o_mk0, o_mk1, o_mk2, o_cur, o_gscore, o_gt;
+    int x_bytes;   // scratch area
+    int o_stat, o_llo, o_llen, o_lraw, o_lstr, o_lbase, o_maxv, o_unk;
+    int o_rhit, o_rab, o_x;
+    int o_hkey, o_hval, o_clid, o_mk0, o_mk1, o_mk2, o_clhead, o_cltail, o_gscore, o_gu, o_gt, o_gnext, o_gloc;
 };
 
 struct FastArgs {
@@ -100,8 +105,12 @@ struct FastArgs {
     FastCfg cfg;
     unsigned long long *wq;        // work-queue head of this launch
     int64_t n_work, work_base;     // contig range ...
-    const int *work_list;          // ... or explicit list
-    int *fb_list;                  // fallback list (ctr->n_fallback entries): contigs for the exact pipeline
+    const int *work_list;          // ... or explicit list, whose length may live on the device:
+    const unsigned long long *n_work_dev;   // (second pass: the first pass's fallback count)
+    int *fb_list;                  // contigs that overflowed a capacity of this pass's slice (next pass) ...
+    unsigned long long *fb_count;  // ... and their number
+    int *fb_final;                 // contigs for the exact pipeline (guard band, > 32 loci, long genes, ...)
+    unsigned long long *fb_final_count;
     const int *anc;                // [anc_rows][n_nodes]: l-th ancestor of every node (row 0 = identity)
     int anc_rows;
     double guard;                  // guard band of the decision compares (1e-12)
@@ -110,7 +119,7 @@ struct FastArgs {
     const uint16_t *plan_data;
     char *scratch;                 // 16 * Kcap bytes per resident warp (exact recomputation of near-threshold groups)
 };
-int fast_layout(FastCfg &F, int Kcap, int Ccap, int Tcap, int Ncap, bool annotations);
+int fast_layout(FastCfg &F, int Kcap, int Mcap, int Ccap, int Tcap, int Ncap, int Scap);
 int fast_warps_per_cta();
 int fast_ctas_per_sm(const FastCfg &F, bool packed, size_t smem_per_sm);
 cudaError_t launch_fast(const FastArgs &a, bool packed, int grid, cudaStream_t s);

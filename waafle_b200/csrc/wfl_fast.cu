@@ -7,25 +7,28 @@
 // raise_taxonomy :431-445, evaluate_contig :566-583, explain_one/two :585-619, meld_one/two :621-676,
 // LGT checks :678-744.
 //
-// How it differs from the exact pipeline (wfl_pipeline.cu):
-//  * per taxonomy level the contig's hits are re-streamed ONE LOCUS AT A TIME from global memory (HBM on the
-//    first pass, L2 afterwards) into a small record buffer; no per-hit or per-record state survives a locus, so
-//    the slice is ~10 KB whatever the hit count, and a lift is "the same pass with the next row of the
-//    ancestor table" (waafle_orgscorer.py:431-445 re-bins site arrays by parent: at level l the envelope of
-//    clade c is over the hits whose l-th ancestor is c);
-//  * gene scores are the CLOSED FORM of the envelope integral, sum_j v_j * |I_j \ union of better hits| / n
-//    (records picked in descending score order, union kept as one interval; a gap sends the group to a
-//    generic endpoint sweep).  numpy's pairwise rounding is not reproduced, so the value is within ~1e-14
-//    of np.mean; instead every DECISION is protected by a guard band:
-//      - a gene score within 1e-12 of a threshold it is compared with (k1, k2, 1e-6) is recomputed
-//        exactly, in numpy's pairwise order, by the pipeline's own group_mean();
-//      - a rank within 1e-12 of the best rank (arg-max) or of best - range (meld set) cannot be settled
-//        locally: the contig is handed to the exact pipeline (fallback list);
-//    so calls / clades / synteny are bit-exact and crit / rank agree to <= 1e-12 (north_star tolerance).
-//  * clades are handled through a per-level open-addressing hash (dense handles in first-seen order); every
-//    tie-break that the reference resolves by name order uses the node index explicitly.
-// Anything the slice cannot hold (too many loci / records per locus / clades / groups / pairs), long genes,
-// --min-overlap <= 0 and malformed input go to the fallback list and are scored by the exact pipeline.
+// How it works (and differs from the exact pipeline, wfl_pipeline.cu):
+//  * once per contig: the hit spans are staged in shared memory, one pass per locus appends the attached hits
+//    (records: hit index + python slice, locus-major), and every locus' records are put in DESCENDING SCORE order
+//    (skipped when they already are: the front end's packer delivers hits sorted by score);
+//  * per taxonomy level, per locus: the records are streamed in score order; each record's clade (the level's row of
+//    the ancestor table: a lift re-bins the site arrays by parent, waafle_orgscorer.py:431-445) gets a dense handle
+//    from a shared-memory hash, and the clade's running ENVELOPE STATE for this locus -- the union of its better hits
+//    as one interval and sum v * (newly covered sites) -- is updated in place.  That sum / n is the closed form of
+//    np.mean of the site array (:371-382, :399-406); no grouping sort, no per-group scan.  A hit that leaves a gap
+//    marks the group for a generic endpoint sweep;
+//  * numpy's pairwise rounding is not reproduced, so the value is within ~1e-14 of np.mean; instead every DECISION
+//    is protected by a guard band:
+//      - a gene score within 1e-12 of a threshold it is compared with (k1, k2, 1e-6) is recomputed exactly, in
+//        numpy's pairwise order, by the pipeline's own group_mean();
+//      - a rank within 1e-12 of the best rank (arg-max) or of best - range (meld set) cannot be settled locally:
+//        the contig is handed to the exact pipeline;
+//    so calls / clades / synteny are bit-exact and crit / rank agree to <= 1e-12 (north_star tolerance);
+//  * gene-score rows are per-clade linked lists of (locus, score) in locus order; every tie-break the reference
+//    resolves by name order uses the node index explicitly (handles are arbitrary labels).
+// Anything the slice cannot hold (too many loci / records / clades / groups / pairs) is retried by a second launch
+// with a larger slice; long genes, > 32 loci, --min-overlap <= 0, guard-band trips and malformed input go to the
+// exact pipeline.
 #include "wfl_warp_common.cuh"
 
 namespace wfl {
@@ -35,6 +38,10 @@ namespace {
 constexpr int FAST_WPC = 4;     // warps (= contigs in flight) per CTA
 constexpr int EMPTY_KEY = -1;
 constexpr int GMAX = 32;        // retained loci per contig: gene bitmasks are one 32-bit word
+constexpr int NONE16 = 0xffff;
+#ifndef WFL_FAST_CPSM
+#define WFL_FAST_CPSM 4         // resident CTAs per SM the kernel is compiled for (register budget)
+#endif
 
 #define SM(T, off) (reinterpret_cast<T *>(slice + (off)))
 
@@ -55,48 +62,37 @@ __device__ __forceinline__ bool overlap_ok(int hmin, int hmax, int lmin, int lma
     return num / den >= mo;
 }
 
-// Exact np.mean of the group's site array (numpy pairwise order) through the pipeline's K2 code: the group's records are
-// copied to a scratch area as the int / double arrays group_mean() walks.  Cold: near-threshold groups only.
-__device__ __noinline__ double group_mean_exact(const FastArgs &a, char *scratch, int Kcap, const double *bv, const u32 *bab,
-                                                const u16 *bord, int rs, int re, int n) {
-    int *ra = reinterpret_cast<int *>(scratch), *rb = ra + Kcap;
-    double *rv = reinterpret_cast<double *>(rb + Kcap);
-    const int k = re - rs;
-#pragma unroll 1
-    for (int j = 0; j < k; ++j) {
-        const int r = bord[rs + j];
-        const u32 ab = bab[r];
-        ra[j] = (int)(ab & 0xffffu);
-        rb[j] = (int)(ab >> 16);
-        rv[j] = bv[r];
-    }
-    const PlanEntry pe = a.plan_index[n];
-    return group_mean(ra, rb, rv, 0, k, n, false, pe.k8, a.plan_data + pe.off, (int)pe.nleaf);
-}
-
 // Per-level view of a contig for the search routines (all pointers into the warp's slice).
 struct FLevel {
     int G, T, t_unk;         // t_unk: handle of the spiked Unknown (dense row unk_row), -1 if none
     u32 um;                  // non-ignored loci
     int nun;
-    const u16 *goff;         // groups of locus i: [goff[i], goff[i+1]), ascending handle
-    const u16 *g_t;
+    const u16 *cl_head;      // first group of each clade; groups of a clade are linked in locus order
+    const u16 *g_next;
+    const u8 *g_loc;
     const double *g_score;
     const double *unk_row;
     const int *cl_id;
     const u32 *mk[3];        // per clade gene bitmasks: score >= k1 / k2 / 1e-6
     const int *l_len;
+    const int *cl_par;       // two-clade search with sister penalty: parent of every LISTED clade of the level, else -1
 };
 
-// gene score of clade handle t at locus i (0 where the clade has no entry, waafle_orgscorer.py:404-405)
-__device__ __forceinline__ double score_at(const FLevel &L, int t, int i) {
-    if (t == L.t_unk) return L.unk_row[i];
-    int p = L.goff[i];
-    const int e = L.goff[i + 1];
+// gene-score row of one clade, walked in locus order (0 where the clade has no entry, waafle_orgscorer.py:404-405)
+struct RowWalk {
+    int p;
+    bool dense;
+    __device__ __forceinline__ void open(const FLevel &L, int t) {
+        dense = t == L.t_unk;
+        p = dense ? NONE16 : (int)L.cl_head[t];
+    }
+    __device__ __forceinline__ double at(const FLevel &L, int i) {
+        if (dense) return L.unk_row[i];
 #pragma unroll 1
-    while (p < e && (int)L.g_t[p] < t) ++p;
-    return (p < e && (int)L.g_t[p] == t) ? L.g_score[p] : 0.0;
-}
+        while (p != NONE16 && (int)L.g_loc[p] < i) p = L.g_next[p];
+        return (p != NONE16 && (int)L.g_loc[p] == i) ? L.g_score[p] : 0.0;
+    }
+};
 
 // Contig.score (waafle_orgscorer.py:447-461) over the non-ignored loci: crit = min, rank = np.mean (n <= 32 values:
 // numpy sums n < 8 sequentially, otherwise eight strided accumulators, the fixed tree, then the tail).
@@ -107,12 +103,15 @@ __device__ __noinline__ double row_stats(const FLevel &L, int t1, int t2, double
     u32 bits = L.um;
     const int body = n < 8 ? 0 : (n & ~7);
     int idx = 0;
+    RowWalk w1, w2;
+    w1.open(L, t1);
+    w2.open(L, t2 >= 0 ? t2 : t1);
 #pragma unroll 1
     while (bits) {
         const int i = __ffs(bits) - 1;
         bits &= bits - 1;
-        double v = score_at(L, t1, i);
-        if (t2 >= 0) v = fmax(v, score_at(L, t2, i));
+        double v = w1.at(L, i);
+        if (t2 >= 0) v = fmax(v, w2.at(L, i));
         crit = fmin(crit, v);
         if (idx < body) {
             const int j = idx & 7;
@@ -186,8 +185,7 @@ __device__ __noinline__ void eval_two_fast(const FLevel &L, const DevTax &tax, c
 #pragma unroll 1
         for (int t = 0; t < L.T && ok; ++t) {
             if (t == ev.t1 || t == ev.t2) continue;
-            const int id = L.cl_id[t];
-            const int px = tax.listed[id] ? tax.parent[id] : -1;   // get_sisters works on the taxonomy file's rows
+            const int px = L.cl_par[t];   // get_sisters works on the taxonomy file's rows
             const bool s1 = px == p1, s2 = (px == p2) && !ev.dir;
             if (!s1 && !s2) continue;
             const u32 ms = msis[t];
@@ -198,44 +196,85 @@ __device__ __noinline__ void eval_two_fast(const FLevel &L, const DevTax &tax, c
     ev.ok = ok;
 }
 
-// Warp-cooperative get-or-insert into the level's clade hash; returns the dense handle (first-seen order: lanes of one
-// call are inserted in lane order, so handles -- and with them the group order and every sum -- are deterministic).
-__device__ __forceinline__ int clade_handle(int *hkey, u16 *hval, int *cl_id, u32 *mk0, u32 *mk1, u32 *mk2, int cmask, int Tcap,
-                                            int &T, u32 i0, u32 i1, u32 i2, int key, bool active, bool &ovf) {
+// Dense handle of a clade in the level's shared-memory hash (get-or-insert).  Handles are arbitrary labels (insertion
+// order of a race); nothing downstream depends on their order.  All lanes call it (inactive lanes pass active = false).
+__device__ __forceinline__ int clade_handle(int *hkey, u16 *hval, int *cl_id, u32 *mk0, u32 *mk1, u32 *mk2, u16 *cl_head,
+                                            u16 *cl_tail, int *t_count, int cmask, int Tcap, u32 i0, u32 i1, u32 i2, int key,
+                                            bool active, bool &ovf) {
     u32 slot = hash32(key) & (u32)cmask;
-    int handle = 0;
-    bool done = !active;
+    bool fail = false;
+    if (active) {
+        int probe = 0;
 #pragma unroll 1
-    for (int it = 0;; ++it) {
-        if (__all_sync(FULL, done)) break;
-        if (it > 2 * cmask + 2) ovf = true;
-        if (__any_sync(FULL, ovf)) break;
-        const int cur = done ? 0 : hkey[slot];
-        if (!done && cur == key) { handle = hval[slot]; done = true; }
-        const bool want = !done && cur == EMPTY_KEY;
-        const u32 wm = __ballot_sync(FULL, want);
-        if (wm) {
-            u32 peers = 0;
-            if (want) peers = __match_any_sync(wm, slot);
-            const bool leader = want && (peers & lt_mask()) == 0;
-            const u32 lm = __ballot_sync(FULL, leader);
-            if (leader) {
-                const int hnew = T + __popc(lm & lt_mask());
+        for (; probe <= cmask; ++probe) {
+            const int old = atomicCAS(&hkey[slot], EMPTY_KEY, key);
+            if (old == EMPTY_KEY) {   // inserted: new clade of this level
+                const int hnew = atomicAdd(t_count, 1);
                 if (hnew < Tcap) {
-                    hkey[slot] = key;
-                    hval[slot] = (u16)hnew;
                     cl_id[hnew] = key;
                     mk0[hnew] = i0; mk1[hnew] = i1; mk2[hnew] = i2;
+                    cl_head[hnew] = cl_tail[hnew] = (u16)NONE16;
+                    hval[slot] = (u16)hnew;
                 } else {
-                    ovf = true;
+                    hval[slot] = 0;
+                    fail = true;
                 }
+                break;
             }
-            T += __popc(lm);
-            __syncwarp();
+            if (old == key) break;
+            slot = (slot + 1) & (u32)cmask;
         }
-        if (!done && !want && cur != key) slot = (slot + 1) & (u32)cmask;   // occupied by another clade
+        if (probe > cmask) fail = true;
+        if (fail) ovf = true;
     }
-    return handle;
+    __syncwarp();
+    return (active && !fail) ? (int)hval[slot] : 0;
+}
+
+// Generic envelope integral of one (clade, locus) group whose better hits leave a gap: the group's records are the records
+// [r0, r0 + k) of the locus whose clade of this level is `clade`; they are gathered into the warp's global scratch (slices and
+// scores) and swept over their distinct endpoints.  Also serves the exact recomputation (numpy pairwise order) of a score
+// that falls inside the guard band.  Cold.
+template <class H>
+__device__ __noinline__ double group_slow(const FastArgs &a, const H &hits, char *scratch, int Kcap, const u16 *rec_hit,
+                                          const u32 *rec_ab, long long h0, int r0, int k, const int *anc, int clade, int n,
+                                          bool exact) {
+    int *ra = reinterpret_cast<int *>(scratch), *rb = ra + Kcap;
+    double *rv = reinterpret_cast<double *>(rb + Kcap);
+    int m = 0;
+#pragma unroll 1
+    for (int j = 0; j < k && m < Kcap; ++j) {
+        const long long h = h0 + rec_hit[r0 + j];
+        if (anc[hits.taxon(h)] != clade) continue;
+        const u32 ab = rec_ab[r0 + j];
+        const double sc = a.b.hit_score[h];
+        ra[m] = (int)(ab & 0xffffu);
+        rb[m] = (int)(ab >> 16);
+        rv[m] = sc > 0.0 ? sc : 0.0;
+        ++m;
+    }
+    if (exact) {
+        const PlanEntry pe = a.plan_index[n];
+        return group_mean(ra, rb, rv, 0, m, n, true, pe.k8, a.plan_data + pe.off, (int)pe.nleaf);   // descending scores
+    }
+    double sum = 0.0;
+#pragma unroll 1
+    for (int e2 = 0; e2 < 2 * m; ++e2) {
+        const int e = (e2 & 1) ? rb[e2 >> 1] : ra[e2 >> 1];
+        bool dup = false;
+        int nx = 0x7fffffff;
+        double mx = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < m; ++q) {
+            const int qa = ra[q], qb = rb[q];
+            if (qa <= e && e < qb) mx = fmax(mx, rv[q]);
+            if (qa > e) nx = min(nx, qa);
+            if (qb > e) nx = min(nx, qb);
+            dup |= (qa == e && 2 * q < e2) || (qb == e && 2 * q + 1 < e2);
+        }
+        if (!dup && mx > 0.0 && nx != 0x7fffffff) sum += mx * (double)(nx - e);
+    }
+    return sum / (double)n;
 }
 
 // ascending node index order for the melded member lists (the exact pipeline emits them in handle == name order)
@@ -274,6 +313,7 @@ __device__ __forceinline__ void write_result_fast(const FastArgs &a, long long c
 }
 
 // hit columns in the two wire formats (include/waafle_b200.h: wfl_batch / wfl_packed_batch)
+// flags: bit 0 = scov_modified >= --min-scov (waafle_orgscorer.py:362), bit 1 = minus strand
 template <bool PACKED>
 struct Hits;
 template <>
@@ -281,12 +321,10 @@ struct Hits<false> {
     const DevBatch &b;
     double min_scov;
     __device__ __forceinline__ void span(long long h, int &q1, int &q2) const { q1 = b.hit_qstart[h]; q2 = b.hit_qend[h]; }
-    // (scov ok, strand, taxon) of a hit whose span already overlaps the locus
-    __device__ __forceinline__ bool rest(long long h, signed char &hs, int &tx) const {
-        hs = b.hit_strand[h];
-        tx = b.hit_taxon[h];
-        return b.hit_scov[h] >= min_scov;   // waafle_orgscorer.py:362
+    __device__ __forceinline__ u8 flags(long long h) const {
+        return (u8)((b.hit_scov[h] >= min_scov ? 1 : 0) | (b.hit_strand[h] == '-' ? 2 : 0));
     }
+    __device__ __forceinline__ int taxon(long long h) const { return b.hit_taxon[h]; }
     __device__ __forceinline__ u32 sysmask(long long h) const { return b.hit_sysmask[h]; }
 };
 template <>
@@ -294,19 +332,18 @@ struct Hits<true> {
     const DevBatch &b;
     double min_scov;
     __device__ __forceinline__ void span(long long h, int &q1, int &q2) const { q1 = b.hit_qstart16[h]; q2 = b.hit_qend16[h]; }
-    __device__ __forceinline__ bool rest(long long h, signed char &hs, int &tx) const {
+    __device__ __forceinline__ u8 flags(long long h) const {   // the host applied the scov filter while packing
         const u32 w = b.hit_tax16[h];
-        hs = (w & 0x4000u) ? '-' : '+';
-        tx = (int)(w & 0x3fffu);
-        return (w & 0x8000u) != 0u;         // host applied scov_modified >= min_scov while packing
+        return (u8)(((w >> 15) & 1u) | (((w >> 14) & 1u) << 1));
     }
+    __device__ __forceinline__ int taxon(long long h) const { return (int)(b.hit_tax16[h] & 0x3fffu); }
     __device__ __forceinline__ u32 sysmask(long long h) const { return b.hit_sysmask8[h]; }
 };
 
 }  // namespace
 
 template <bool PACKED>
-__global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastArgs a) {
+__global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs(const FastArgs a) {
     extern __shared__ __align__(16) char fast_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     char *slice = fast_smem + (size_t)wid * a.cfg.slice_bytes;
@@ -321,39 +358,47 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
 
     int *l_lo = SM(int, F.o_llo), *l_len = SM(int, F.o_llen), *l_raw = SM(int, F.o_lraw);
     signed char *l_str = SM(signed char, F.o_lstr);
-    u16 *goff = SM(u16, F.o_goff);
+    u16 *l_base = SM(u16, F.o_lbase);
     double *maxv = SM(double, F.o_maxv), *unk_row = SM(double, F.o_unk);
-    double *bv = SM(double, F.o_bv);
-    u32 *bab = SM(u32, F.o_bab);
-    int *bcl = SM(int, F.o_bcl);          // clade ids of the buffered records; dead once handles are known ...
-    u16 *bord = SM(u16, F.o_bcl);         // ... then the multisplit order and
-    u16 *grs = bord + F.Kcap;             // the group starts of the locus live there
-    u16 *bt = SM(u16, F.o_bt);
-    int *bh = SM(int, F.o_bh);
+    // level-invariant records (hit x locus matches), locus-major, descending score inside a locus: hit index and python
+    // slice [a, b) packed a | b << 16
+    u16 *rec_hit = SM(u16, F.o_rhit);
+    u32 *rec_ab = SM(u32, F.o_rab);
+    char *xs = SM(char, F.o_x);           // scratch: rank cache / two-clade candidates + survivors
+    // staging of the contig's hit spans / flags while the records are bucketed (aliases the per-level arrays)
+    u32 *hsp = SM(u32, F.o_hkey);
+    u32 *hmk = hsp + F.Hcap;              // loci each hit is attached to
+    // per-level arrays: clade hash and table, (clade, locus) groups
     int *hkey = SM(int, F.o_hkey);
     u16 *hval = SM(u16, F.o_hval);
     int *cl_id = SM(int, F.o_clid);
     u32 *mk0 = SM(u32, F.o_mk0), *mk1 = SM(u32, F.o_mk1), *mk2 = SM(u32, F.o_mk2);
-    u16 *cur = SM(u16, F.o_cur);
-    double *g_score = SM(double, F.o_gscore);
-    u16 *g_t = SM(u16, F.o_gt);
+    u16 *cl_head = SM(u16, F.o_clhead), *cl_tail = SM(u16, F.o_cltail);
+    double *g_score = SM(double, F.o_gscore);   // running sum v * (newly covered sites) while the locus streams, then the score
+    u32 *g_u = SM(u32, F.o_gu);                 // [Kcap] union of the better hits of the CURRENT locus' groups: ua | ub << 16
+    u16 *g_t = SM(u16, F.o_gt), *g_next = SM(u16, F.o_gnext);
+    u8 *g_loc = SM(u8, F.o_gloc);               // locus of the group (bit 7: a hit left a gap -> generic sweep)
+    unsigned long long *stat = SM(unsigned long long, F.o_stat);   // per-warp counters, flushed once at exit
+    int *t_count = reinterpret_cast<int *>(stat + 8);              // clades of the current level
     char *scratch = a.scratch + ((size_t)blockIdx.x * FAST_WPC + wid) * (size_t)F.Kcap * 16;
-
-    unsigned long long st_pairs = 0, st_groups = 0, st_levels = 0, st_ptest = 0, st_pscore = 0, st_done = 0, st_refined = 0,
-                       st_trips = 0;
+    enum { ST_PAIRS, ST_GROUPS, ST_LEVELS, ST_PTEST, ST_PSCORE, ST_DONE, ST_REFINED, ST_TRIPS, ST_N };
+    if (lane < ST_N) stat[lane] = 0;
+    __syncwarp();
+    const unsigned long long n_work = a.n_work_dev ? *a.n_work_dev : (unsigned long long)a.n_work;
 
 #pragma unroll 1
     for (;;) {
         long long c = -1;
         if (lane == 0) {
             const unsigned long long w = atomicAdd(a.wq, 1ull);
-            if ((long long)w < a.n_work) c = a.work_list ? (long long)a.work_list[w] : a.work_base + (long long)w;
+            if (w < n_work) c = a.work_list ? (long long)a.work_list[w] : a.work_base + (long long)w;
         }
         c = __shfl_sync(FULL, c, 0);
         if (c < 0) break;
         const long long h0 = a.b.hit_off[c], l0 = a.b.locus_off[c];
         const int H = (int)(a.b.hit_off[c + 1] - h0), Graw = (int)(a.b.locus_off[c + 1] - l0);
         bool fallback = false, trip = false;
+        int reason = 0;   // why the contig goes to the next pass: 0 loci, 1 hits, 2 coordinates, 3 records, 4 clades, 5 groups, 6 pairs, 7 guard
         FOut R{WFL_CALL_UNCLASSIFIED, 0, -1, -1, -1, -1, -1, 0, 0, H > 0 ? P.p.jump_taxonomy : 0, 0, 0.0, 0.0};
         bool finished = false;
 
@@ -395,67 +440,137 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
         // a locus without an entry scores 0 (waafle_orgscorer.py:404-405): its mask bit is (0 >= threshold)
         const u32 init0 = thr3[0] <= 0.0 ? allG : 0u, init1 = thr3[1] <= 0.0 ? allG : 0u, init2 = 0u;
 
+        // ---- K1, once per contig (level-invariant): which hit is attached to which locus (attach_hits :359-369) ----
+        int M = 0;
+        if (!fallback && H > 0 && G > 0) {
+            if (H > F.Hcap) {
+                fallback = true;
+                reason = 1;
+            } else {
+                // (a) one pass over the hits: span, filter flags and the mask of the loci each hit is attached to
+                bool big = false;
+                const u8 fmask = P.p.stranded ? 3 : 1;
+#pragma unroll 2
+                for (int base = 0; base < H; base += 32) {
+                    const int h = base + lane;
+                    if (h < H) {
+                        int q1, q2;
+                        hits.span(h0 + h, q1, q2);
+                        const int hmin = min(q1, q2), hmax = max(q1, q2);
+                        big |= hmin < 0 || hmax > 65535;
+                        const u8 fl = hits.flags(h0 + h);
+                        u32 mb = 0;
+                        if (fl & 1) {   // scov_modified >= --min-scov (:362)
+#pragma unroll 1
+                            for (int i = 0; i < G; ++i) {
+                                const int lmin = l_lo[i], llen = l_len[i], lmax = lmin + llen - 1;
+                                if (lmin > hmax || hmin > lmax) continue;
+                                if (P.p.stranded) {   // hit.sstrand == locus.strand (:365)
+                                    const signed char ls = l_str[i];
+                                    if (!((ls == '-' && (fl & 2)) || (ls == '+' && !(fl & 2)))) continue;
+                                }
+                                if (overlap_ok(hmin, hmax, lmin, lmax, llen, P.p.min_overlap)) mb |= 1u << i;
+                            }
+                        }
+                        hsp[h] = (u32)(hmin & 0xffff) | ((u32)(hmax & 0xffff) << 16);
+                        hmk[h] = mb;
+                    }
+                }
+                (void)fmask;
+                if (__any_sync(FULL, big)) { fallback = true; reason = 2; }   // spans are staged in 16 bits
+                __syncwarp();
+            }
+            // (b) one compaction pass per locus over the staged masks: records come out locus-major, hit order inside
+#pragma unroll 1
+            for (int i = 0; i < G && !fallback; ++i) {
+                const int lmin = l_lo[i], llen = l_len[i];
+                if (lane == 0) l_base[i] = (u16)M;
+                const int m0 = M;
+#pragma unroll 2
+                for (int base = 0; base < H; base += 32) {
+                    const int h = base + lane;
+                    const bool mt = h < H && ((hmk[h] >> i) & 1u);
+                    const u32 m = __ballot_sync(FULL, mt);
+                    if (mt) {
+                        const int slot = M + __popc(m & lt_mask());
+                        if (slot < F.Mcap) {
+                            const u32 sp = hsp[h];
+                            const int hmin = (int)(sp & 0xffffu), hmax = (int)(sp >> 16);
+                            rec_hit[slot] = (u16)h;
+                            // python slice [h1 : h2+1] of the site array (:373-382)
+                            rec_ab[slot] = (u32)max(0, hmin - lmin) | ((u32)(min(llen - 1, hmax - lmin) + 1) << 16);
+                        }
+                    }
+                    M += __popc(m);
+                }
+                if (M > F.Mcap || M - m0 > F.Kcap) { fallback = true; reason = 3; }
+            }
+            if (lane == 0) l_base[G] = (u16)M;
+            __syncwarp();
+            // (c) every locus' records in DESCENDING SCORE order (ties: hit order), once per contig: the level loop streams
+            // them in that order, so that a clade's envelope only ever grows by "newly covered sites x score".  Loci that
+            // arrive sorted (the front end's packer sorts the hits of a contig by score) skip the rank-by-counting sort.
+            if (!fallback) {
+                double *tv = reinterpret_cast<double *>(hsp);                      // [Kcap] scores of the locus
+                u16 *th = reinterpret_cast<u16 *>(tv + F.Kcap);                    // [Kcap] sorted hit indices
+                u32 *tab = reinterpret_cast<u32 *>(th + F.Kcap + (F.Kcap & 1));    // [Kcap] sorted slices
+#pragma unroll 1
+                for (int i = 0; i < G; ++i) {
+                    const int r0 = l_base[i], k = (int)l_base[i + 1] - r0;
+                    if (k < 2) continue;
+#pragma unroll 2
+                    for (int j = lane; j < k; j += 32) tv[j] = a.b.hit_score[h0 + rec_hit[r0 + j]];
+                    __syncwarp();
+                    bool sorted = true;
+#pragma unroll 1
+                    for (int j = lane; j + 1 < k; j += 32) sorted &= tv[j] >= tv[j + 1];
+                    if (__all_sync(FULL, sorted)) continue;
+#pragma unroll 1
+                    for (int j = lane; j < k; j += 32) {
+                        const double v = tv[j];
+                        int rk = 0;
+#pragma unroll 4
+                        for (int q = 0; q < k; ++q) {
+                            const double vq = tv[q];
+                            rk += (vq > v) || (vq == v && q < j);
+                        }
+                        th[rk] = rec_hit[r0 + j];
+                        tab[rk] = rec_ab[r0 + j];
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int j = lane; j < k; j += 32) {
+                        rec_hit[r0 + j] = th[j];
+                        rec_ab[r0 + j] = tab[j];
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
         int iter = 0;
 #pragma unroll 1
         while (!fallback && !finished && H > 0 && G > 0) {
             // ============================ one taxonomy level ============================
             const int *anc = a.anc + (size_t)min(R.lifts, a.anc_rows - 1) * (size_t)tax.n_nodes;
-            int T = 0, N = 0;
+            int N = 0, ovf_reason = 4;
             bool ovf = false;
+            if (lane == 0) *t_count = 0;
 #pragma unroll 1
             for (int s = lane; s <= F.cmask; s += 32) hkey[s] = EMPTY_KEY;
             __syncwarp();
             if (spike)   // "Unknown" is a clade of every level (waafle_orgscorer.py:416-418): handle 0
-                (void)clade_handle(hkey, hval, cl_id, mk0, mk1, mk2, F.cmask, F.Tcap, T, 0u, 0u, 0u, tax.unknown, lane == 0, ovf);
+                (void)clade_handle(hkey, hval, cl_id, mk0, mk1, mk2, cl_head, cl_tail, t_count, F.cmask, F.Tcap, 0u, 0u, 0u,
+                                   tax.unknown, lane == 0, ovf);
             const int t_unk = spike ? 0 : -1;
-            ++st_levels;
+            if (lane == 0) ++stat[ST_LEVELS];
 
 #pragma unroll 1
-            for (int i = 0; i < G && !ovf; ++i) {
-                const int lmin = l_lo[i], llen = l_len[i], lmax = lmin + llen - 1;
-                const signed char ls = l_str[i];
-                // ---- K1: stream the contig's hits, keep the ones attached to locus i (attach_hits :359-369) ----
-                int k = 0;
-#pragma unroll 1
-                for (int base = 0; base < H; base += 32) {
-                    const int h = base + lane;
-                    bool mt = false;
-                    int hmin = 0, hmax = 0, tx = 0;
-                    if (h < H) {
-                        int q1, q2;
-                        hits.span(h0 + h, q1, q2);
-                        hmin = min(q1, q2);
-                        hmax = max(q1, q2);
-                        if (!(lmin > hmax || hmin > lmax)) {
-                            signed char hs;
-                            mt = hits.rest(h0 + h, hs, tx) && !(P.p.stranded && hs != ls) &&
-                                 overlap_ok(hmin, hmax, lmin, lmax, llen, P.p.min_overlap);
-                        }
-                    }
-                    const u32 m = __ballot_sync(FULL, mt);
-                    if (!m) continue;
-                    if (mt) {
-                        const int slot = k + __popc(m & lt_mask());
-                        if ((u32)tx >= (u32)tax.n_nodes) {
-                            ovf = true;   // malformed input: the exact pipeline reports it
-                        } else if (slot < F.Kcap) {
-                            const double sc = a.b.hit_score[h0 + h];
-                            // python slice [h1 : h2+1] of the site array (:373-382); sites start at 0 (np.zeros)
-                            const int s1 = max(0, hmin - lmin), e1 = min(llen - 1, hmax - lmin) + 1;
-                            bv[slot] = sc > 0.0 ? sc : 0.0;
-                            bab[slot] = (u32)s1 | ((u32)e1 << 16);
-                            bcl[slot] = anc[tx];
-                            if (S > 0) bh[slot] = h;
-                        }
-                    }
-                    k += __popc(m);
-                }
-                if (k > F.Kcap) ovf = true;
-                ovf = __any_sync(FULL, ovf);
-                if (ovf) break;
-                __syncwarp();
-                if (iter == 0) st_pairs += (unsigned long long)k;
-                if (lane == 0) goff[i] = (u16)N;
+            for (int i = 0; i < G; ++i) {
+                const int llen = l_len[i];
+                const int r0 = l_base[i], k = (int)l_base[i + 1] - r0;
+                const int N0 = N;
+                if (iter == 0 && lane == 0) stat[ST_PAIRS] += (unsigned long long)k;
                 if (k == 0) { if (lane == 0) maxv[i] = 0.0; continue; }
 
                 // ---- K3: annotation winners, level-independent (score_hit :384-392): last hit with the max score ----
@@ -466,10 +581,11 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                         long long bw = -1;
 #pragma unroll 1
                         for (int r = lane; r < k; r += 32) {
-                            const double sc = bv[r];
-                            if (((hits.sysmask(h0 + bh[r]) >> s2) & 1u) && sc >= P.ann_thr) {
+                            const int hh = rec_hit[r0 + r];
+                            const double sc = a.b.hit_score[h0 + hh];
+                            if (((hits.sysmask(h0 + hh) >> s2) & 1u) && sc >= P.ann_thr) {
                                 const u64 sb = dbits(sc);
-                                if (sb >= bb) { bb = sb; bw = bh[r]; }
+                                if (sb > bb || (sb == bb && hh > bw)) { bb = sb; bw = hh; }
                             }
                         }
                         const u64 mx = warp_max_u64(bb);
@@ -478,120 +594,157 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                     }
                 }
 
-                // ---- clade handles of the records (dense, first-seen order) ----
+                // ---- K2: stream the locus' records in score order; every clade's envelope state grows in place ----
+                // (the next tile's hit data is requested before the current tile is processed)
+                u32 ab_n = 0;
+                int tx_n = 0;
+                double sc_n = 0.0;
+                if (lane < k) {
+                    const long long h = h0 + rec_hit[r0 + lane];
+                    ab_n = rec_ab[r0 + lane];
+                    tx_n = hits.taxon(h);
+                    sc_n = a.b.hit_score[h];
+                }
 #pragma unroll 1
                 for (int base = 0; base < k; base += 32) {
-                    const int r = base + lane;
-                    const int hd = clade_handle(hkey, hval, cl_id, mk0, mk1, mk2, F.cmask, F.Tcap, T, init0, init1, init2,
-                                                r < k ? bcl[r] : 0, r < k, ovf);
-                    if (r < k) bt[r] = (u16)hd;
+                    const int j = base + lane;
+                    bool act = j < k;
+                    const u32 ab = ab_n;
+                    const int tx = tx_n;
+                    const double sc = sc_n;
+                    if (j + 32 < k) {
+                        const long long h = h0 + rec_hit[r0 + j + 32];
+                        ab_n = rec_ab[r0 + j + 32];
+                        tx_n = hits.taxon(h);
+                        sc_n = a.b.hit_score[h];
+                    }
+                    double v = 0.0;
+                    int cl = tax.root;
+                    if (act) {
+                        if ((u32)tx >= (u32)tax.n_nodes) ovf = true;   // malformed input: the exact pipeline reports it
+                        else cl = R.lifts ? anc[tx] : tx;              // row 0 of the ancestor table is the identity
+                        v = sc > 0.0 ? sc : 0.0;                       // sites start at 0 (np.zeros, :381)
+                    }
+                    const int t = clade_handle(hkey, hval, cl_id, mk0, mk1, mk2, cl_head, cl_tail, t_count, F.cmask, F.Tcap,
+                                               init0, init1, init2, cl, act, ovf);
+                    // with "assign-unknown" the hits of a taxon NAMED Unknown carry no gene score: the spiked row replaces
+                    // gene_scores["Unknown"] (waafle_orgscorer.py:416-418)
+                    if (t == t_unk) act = false;
+                    const u32 peers = __match_any_sync(FULL, act ? t : 0x10000 + lane);
+                    const int leader = __ffs(peers) - 1;
+                    int g = -1;
+                    bool cont = false;
+                    if (act && lane == leader) {   // the clade's group of THIS locus, if an earlier tile opened it
+                        const int tail = cl_tail[t];
+                        if (tail != NONE16 && (int)(g_loc[tail] & 0x3f) == i) { g = tail; cont = true; }
+                    }
+                    const bool newg = act && lane == leader && !cont;
+                    const u32 nm = __ballot_sync(FULL, newg);
+                    if (newg) {
+                        g = N + __popc(nm & lt_mask());
+                        if (g < F.Ncap) {
+                            g_t[g] = (u16)t;
+                            g_loc[g] = (u8)i;
+                            g_next[g] = (u16)NONE16;
+                            const int tail = cl_tail[t];   // rows: groups of a clade linked in locus order
+                            if (tail != NONE16) g_next[tail] = (u16)g; else cl_head[t] = (u16)g;
+                            cl_tail[t] = (u16)g;
+                        }
+                    }
+                    N += __popc(nm);
+                    if (act && N <= F.Ncap) {
+                        g = __shfl_sync(peers, g, leader);
+                        cont = __shfl_sync(peers, (int)cont, leader) != 0;
+                        int ua, ub;
+                        double sum;
+                        bool cplx = false;
+                        u32 rest = peers;
+                        if (cont) {
+                            const u32 u = g_u[g - N0];
+                            ua = (int)(u & 0xffffu);
+                            ub = (int)(u >> 16);
+                            sum = g_score[g];
+                        } else {   // the group opens with its best hit
+                            const u32 ab0 = __shfl_sync(peers, ab, leader);
+                            const double v0 = __shfl_sync(peers, v, leader);
+                            ua = (int)(ab0 & 0xffffu);
+                            ub = (int)(ab0 >> 16);
+                            sum = v0 * (double)(ub - ua);
+                            rest &= rest - 1;
+                        }
+#pragma unroll 1
+                        while (rest) {   // the clade's other hits of this tile, in score order
+                            if (ua == 0 && ub == llen) break;   // the union covers the gene: nothing can be added
+                            const int p = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            const u32 abp = __shfl_sync(peers, ab, p);
+                            const double vp = __shfl_sync(peers, v, p);
+                            if (vp > 0.0) {
+                                const int pa = (int)(abp & 0xffffu), pb = (int)(abp >> 16);
+                                if (pa > ub || pb < ua) {
+                                    cplx = true;   // a gap: the union is no longer one interval
+                                } else {
+                                    const int add = max(0, ua - pa) + max(0, pb - ub);
+                                    if (add) sum += vp * (double)add;
+                                    ua = min(ua, pa);
+                                    ub = max(ub, pb);
+                                }
+                            }
+                        }
+                        if (lane == leader) {
+                            g_u[g - N0] = (u32)ua | ((u32)ub << 16);
+                            g_score[g] = sum;
+                            if (cplx) g_loc[g] |= 0x80;
+                        }
+                    }
+                    // the next tile reads this tile's state: clade_handle() synchronises the warp first
                 }
+                if (N > F.Ncap) { ovf = true; ovf_reason = 5; }
                 ovf = __any_sync(FULL, ovf);
                 if (ovf) break;
                 __syncwarp();
 
-                // ---- group by clade: stable multisplit of the buffer by handle (bcl is dead: bord / grs take its place) ----
-#pragma unroll 1
-                for (int b = lane; b <= T; b += 32) cur[b] = 0;
-                __syncwarp();
-#pragma unroll 1
-                for (int base = 0; base < k; base += 32) {
-                    const int r = base + lane;
-                    const int b = r < k ? (int)bt[r] : T;
-                    const u32 peers = __match_any_sync(FULL, b);
-                    if ((peers & lt_mask()) == 0) cur[b] += (u16)__popc(peers);
-                    __syncwarp();
-                }
-                {
-                    int carry = 0;
-#pragma unroll 1
-                    for (int base = 0; base < T; base += 32) {
-                        const int b = base + lane;
-                        const int cnt = b < T ? (int)cur[b] : 0;
-                        int tot;
-                        const int ex = warp_excl_scan(cnt, tot);
-                        if (b < T) cur[b] = (u16)(carry + ex);
-                        carry += tot;
-                    }
-                }
-                __syncwarp();
-#pragma unroll 1
-                for (int base = 0; base < k; base += 32) {
-                    const int r = base + lane;
-                    const int b = r < k ? (int)bt[r] : T;
-                    const u32 peers = __match_any_sync(FULL, b);
-                    if (r < k) bord[cur[b] + __popc(peers & lt_mask())] = (u16)r;
-                    __syncwarp();
-                    if (r < k && (peers & lt_mask()) == 0) cur[b] += (u16)__popc(peers);
-                    __syncwarp();
-                }
-                // ---- groups = runs of equal handle in bord ----
-                int ng = 0;
-#pragma unroll 1
-                for (int base = 0; base < k; base += 32) {
-                    const int q = base + lane;
-                    bool head = false;
-                    int t = 0;
-                    if (q < k) {
-                        t = bt[bord[q]];
-                        head = q == 0 || t != (int)bt[bord[q - 1]];
-                    }
-                    const u32 m = __ballot_sync(FULL, head);
-                    if (head) {
-                        const int gid = ng + __popc(m & lt_mask());
-                        grs[gid] = (u16)q;
-                        if (N + gid < F.Ncap) g_t[N + gid] = (u16)t;
-                    }
-                    ng += __popc(m);
-                }
-                if (lane == 0) grs[ng] = (u16)k;
-                if (N + ng > F.Ncap) { ovf = true; break; }
-                __syncwarp();
-
-                // ---- K2: gene score of every (clade, locus i) group; masks; per-locus max ----
+                // ---- the locus' groups are complete: gene scores, guard band, masks, per-locus max ----
                 u64 mxb = dbits(0.0);
                 const double dn = (double)llen;
 #pragma unroll 1
-                for (int base = 0; base < ng; base += 32) {
-                    const int j = base + lane;
-                    const bool act = j < ng;
-                    int rs = 0, re = 0, t = 0;
-                    if (act) {
-                        rs = grs[j];
-                        re = grs[j + 1];
-                        t = g_t[N + j];
-                    }
-                    // with "assign-unknown" the hits of a taxon NAMED Unknown carry no gene score: the spiked row
-                    // replaces gene_scores["Unknown"] (waafle_orgscorer.py:416-418)
-                    const bool scored = act && t != t_unk;
+                for (int base = N0; base < N; base += 32) {
+                    const int g = base + lane;
+                    const bool act = g < N;
+                    int t = 0;
+                    bool cplx = false;
                     double sc = 0.0;
-                    if (scored) {
-                        double sum;
-                        if (re - rs == 1) {
-                            const int r = bord[rs];
-                            const u32 ab = bab[r];
-                            sum = bv[r] * (double)((int)(ab >> 16) - (int)(ab & 0xffffu));
-                        } else {
-                            sum = group_integral(bv, bab, bord, rs, re);
-                        }
-                        sc = sum / dn;
+                    if (act) {
+                        t = g_t[g];
+                        cplx = (g_loc[g] & 0x80) != 0;
+                        sc = g_score[g] / dn;
                     }
-                    // guard band: a score this close to a threshold is recomputed in numpy's summation order
-                    const bool near = scored && (fabs(sc - thr3[0]) <= GUARD || fabs(sc - thr3[1]) <= GUARD ||
-                                                 fabs(sc - thr3[2]) <= GUARD);
+                    // groups whose hits left a gap: generic endpoint sweep; scores inside the guard band of a threshold:
+                    // recomputed in numpy's summation order.  Both cold, one lane at a time (global scratch of the warp).
+                    u32 cm = __ballot_sync(FULL, act && cplx);
+#pragma unroll 1
+                    while (cm) {
+                        const int ln = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        if (lane == ln) sc = group_slow(a, hits, scratch, F.Kcap, rec_hit, rec_ab, h0, r0, k, anc, cl_id[t], llen, false);
+                        __syncwarp();
+                    }
+                    const bool near = act && (fabs(sc - thr3[0]) <= GUARD || fabs(sc - thr3[1]) <= GUARD ||
+                                              fabs(sc - thr3[2]) <= GUARD);
                     u32 nm = __ballot_sync(FULL, near);
 #pragma unroll 1
                     while (nm) {
                         const int ln = __ffs(nm) - 1;
                         nm &= nm - 1;
                         if (lane == ln) {
-                            sc = group_mean_exact(a, scratch, F.Kcap, bv, bab, bord, rs, re, llen);
-                            ++st_refined;
+                            sc = group_slow(a, hits, scratch, F.Kcap, rec_hit, rec_ab, h0, r0, k, anc, cl_id[t], llen, true);
+                            atomicAdd(&stat[ST_REFINED], 1ull);
                         }
                         __syncwarp();
                     }
-                    if (act) g_score[N + j] = sc;
-                    if (scored) {
+                    if (act) {
+                        g_score[g] = sc;
+                        g_loc[g] = (u8)i;
                         const u32 bit = 1u << i;
                         mk0[t] = sc >= thr3[0] ? (mk0[t] | bit) : (mk0[t] & ~bit);
                         mk1[t] = sc >= thr3[1] ? (mk1[t] | bit) : (mk1[t] & ~bit);
@@ -604,14 +757,13 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                 }
                 mxb = warp_max_u64(mxb);
                 if (lane == 0) maxv[i] = dbits_inv(mxb);
-                N += ng;
                 __syncwarp();
             }
             ovf = __any_sync(FULL, ovf);
-            if (ovf) { fallback = true; break; }
-            if (lane == 0) goff[G] = (u16)N;
-            st_groups += (unsigned long long)N;
+            if (ovf) { fallback = true; reason = ovf_reason; break; }
+            if (lane == 0) stat[ST_GROUPS] += (unsigned long long)N;
             __syncwarp();
+            const int T = *t_count;
 
             // ---- K4: weak loci (update_gene_scores :407-429) ----
             bool ign = false;
@@ -646,10 +798,13 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
             for (int t = lane; t < T; t += 32) hasroot |= cl_id[t] == tax.root;
             hasroot = __any_sync(FULL, hasroot);
 
-            FLevel L{G, T, t_unk, um, nun, goff, g_t, g_score, unk_row, cl_id, {mk0, mk1, mk2}, l_len};
+            FLevel L{G, T, t_unk, um, nun, cl_head, g_next, g_loc, g_score, unk_row, cl_id, {mk0, mk1, mk2}, l_len, hkey};
 
             // ---- K6: one-clade search (explain_one :585-597) ----
             {
+                // ranks of the passing clades are kept for the meld pass (in the scratch area, if they fit)
+                double *rcache = reinterpret_cast<double *>(xs);
+                const bool cached = T * 8 <= F.x_bytes;
                 u64 bbits = 0;
                 int bid = -1, btl = -1;
                 double bcrit = 0.0;
@@ -658,6 +813,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                     if ((mk0[t] & um) != um) continue;   // crit >= k1
                     double crit;
                     const double rank = row_stats(L, t, -1, &crit);
+                    if (cached) rcache[t] = rank;
                     const u64 b = dbits(rank);
                     if (b > bbits || (b == bbits && cl_id[t] > bid)) { bbits = b; bid = cl_id[t]; btl = t; bcrit = crit; }
                 }
@@ -680,7 +836,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                         bool kept = false;
                         if (t < T && (mk0[t] & um) == um) {
                             double crit;
-                            const double rank = t == tb ? brank : row_stats(L, t, -1, &crit);
+                            const double rank = t == tb ? brank : (cached ? rcache[t] : row_stats(L, t, -1, &crit));
                             const double d = brank - rank;
                             if (t != tb && fabs(d) <= GUARD) near = true;
                             if (P.p.disambiguate_one == 1 && fabs(d - P.p.range) <= GUARD) near = true;
@@ -719,7 +875,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
 
             // ---- K7 / K8: two-clade search (explain_two :599-619, meld_two :633-669, LGT checks :678-744) ----
             {
-                u16 *cand = cur;   // the multisplit cursors are dead
+                u16 *cand = reinterpret_cast<u16 *>(xs);
                 int T2 = 0;
 #pragma unroll 1
                 for (int base = 0; base < T; base += 32) {
@@ -731,9 +887,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                 }
                 __syncwarp();
                 const int NP = T2 * (T2 - 1) / 2;
-                st_ptest += (unsigned long long)NP;
-                // survivors of the mask prefilter live in the (dead) record buffer
-                u16 *s_a = reinterpret_cast<u16 *>(bv), *s_b = s_a + F.Scap;
+                if (lane == 0) stat[ST_PTEST] += (unsigned long long)NP;
+                // survivors of the mask prefilter follow the candidates in the scratch area
+                u16 *s_a = reinterpret_cast<u16 *>(xs + ((2 * F.Tcap + 15) & ~15)), *s_b = s_a + F.Scap;
                 double *s_rank = reinterpret_cast<double *>(s_b + F.Scap);
                 int nsurv = 0;
                 {
@@ -770,8 +926,8 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                         }
                     }
                 }
-                if (nsurv > F.Scap) { fallback = true; break; }
-                st_pscore += (unsigned long long)nsurv;
+                if (nsurv > F.Scap) { fallback = true; reason = 6; break; }
+                if (lane == 0) stat[ST_PSCORE] += (unsigned long long)nsurv;
                 __syncwarp();
                 // exact crit / rank of the survivors; best = last maximal rank in (clade1, clade2) iteration order
                 u64 bbits = 0;
@@ -790,6 +946,14 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                 const long long wy = warp_max_ll((bq >= 0 && bbits == wb && (long long)bx == wx) ? (long long)by : -1);
                 __syncwarp();
                 if (nsurv > 0) {
+                    if (P.p.sister_penalty != 0) {   // parents of the level's listed clades, once (check_sister_penalty :717-744)
+#pragma unroll 2
+                        for (int t = lane; t < T; t += 32) {
+                            const int id = cl_id[t];
+                            hkey[t] = tax.listed[id] ? tax.parent[id] : -1;
+                        }
+                        __syncwarp();
+                    }
                     const int owner = __ffs(__ballot_sync(FULL, bq >= 0 && bbits == wb && (long long)bx == wx && (long long)by == wy)) - 1;
                     const int bp = __shfl_sync(FULL, bq, owner);
                     const int bi = s_a[bp], bj = s_b[bp];
@@ -858,8 +1022,8 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
                             a.o.synteny[l0 + l_raw[lane]] = ign ? '~' : (be.amb & m) ? '*' : (be.A & m) ? 'A' : (be.B & m) ? 'B' : '!';
                         }
                         if (melded) {
-                            // distinct melded clades per side, ascending node index
-                            int *klist = hkey;
+                            // distinct melded clades per side, ascending node index (lists in the dead group scores)
+                            int *klist = reinterpret_cast<int *>(g_score);
 #pragma unroll 1
                             for (int side = 0; side < 2; ++side) {
                                 const u8 *mem = side ? memB : memA;
@@ -896,11 +1060,15 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
         }
         if (H == 0 || G == 0) finished = !fallback;
 
-        if (trip) ++st_trips;
+        if (trip) reason = 7;
+        if (trip && lane == 0) ++stat[ST_TRIPS];
         if (fallback || trip || !finished) {
             if (lane == 0) {
-                const unsigned long long s = atomicAdd(&a.ctr->n_fallback, 1ull);
-                a.fb_list[s] = (int)c;
+                // capacity overflows are worth a second pass with a larger slice; the rest goes straight to the exact pipeline
+                const bool retry = reason == 1 || reason == 3 || reason == 4 || reason == 5 || reason == 6;
+                const unsigned long long s = atomicAdd(retry ? a.fb_count : a.fb_final_count, 1ull);
+                (retry ? a.fb_list : a.fb_final)[s] = (int)c;
+                atomicAdd(&a.ctr->fb_reason[reason & 7], 1ull);
                 // placeholder record (the speculative compaction walks every contig): overwritten by the exact pipeline
                 a.o.call[c] = WFL_CALL_UNCLASSIFIED;
                 a.o.n_mem_a[c] = a.o.n_mem_b[c] = 0;
@@ -908,25 +1076,20 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
             }
         } else {
             if (lane == 0) write_result_fast(a, c, R);
-            ++st_done;
+            if (lane == 0) ++stat[ST_DONE];
         }
         __syncwarp();
     }
+    __syncwarp();
     if (lane == 0) {
-        if (st_pairs) atomicAdd(&a.ctr->matched_pairs, st_pairs);
-        if (st_groups) atomicAdd(&a.ctr->groups, st_groups);
-        if (st_levels) atomicAdd(&a.ctr->levels, st_levels);
-        if (st_ptest) atomicAdd(&a.ctr->pairs_tested, st_ptest);
-        if (st_pscore) atomicAdd(&a.ctr->pairs_scored, st_pscore);
-        if (st_done) atomicAdd(&a.ctr->smem_contigs, st_done);
-        if (st_trips) atomicAdd(&a.ctr->guard_trips, st_trips);
-    }
-    // st_refined lives on whichever lane refined: reduce over the warp
-    {
-        unsigned long long r = st_refined;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
-        if (lane == 0 && r) atomicAdd(&a.ctr->refined_groups, r);
+        if (stat[ST_PAIRS]) atomicAdd(&a.ctr->matched_pairs, stat[ST_PAIRS]);
+        if (stat[ST_GROUPS]) atomicAdd(&a.ctr->groups, stat[ST_GROUPS]);
+        if (stat[ST_LEVELS]) atomicAdd(&a.ctr->levels, stat[ST_LEVELS]);
+        if (stat[ST_PTEST]) atomicAdd(&a.ctr->pairs_tested, stat[ST_PTEST]);
+        if (stat[ST_PSCORE]) atomicAdd(&a.ctr->pairs_scored, stat[ST_PSCORE]);
+        if (stat[ST_DONE]) atomicAdd(&a.ctr->smem_contigs, stat[ST_DONE]);
+        if (stat[ST_TRIPS]) atomicAdd(&a.ctr->guard_trips, stat[ST_TRIPS]);
+        if (stat[ST_REFINED]) atomicAdd(&a.ctr->refined_groups, stat[ST_REFINED]);
     }
 }
 
@@ -934,34 +1097,43 @@ __global__ void __launch_bounds__(32 * FAST_WPC, 4) wfl_fast_contigs(const FastA
 // host side
 // ---------------------------------------------------------------------------------------------
 // Slice layout for given capacities; returns the slice size in bytes (multiple of 16).
-int fast_layout(FastCfg &F, int Kcap, int Ccap, int Tcap, int Ncap, bool annotations) {
+//   Kcap records of one locus, Mcap records of the contig, Ccap clade-hash slots (power of two), Tcap clades and
+//   Ncap (clade, locus) groups per level.  Hcap (hits per contig) follows: the spans are staged over the per-level arrays.
+int fast_layout(FastCfg &F, int Kcap, int Mcap, int Ccap, int Tcap, int Ncap, int Scap) {
     auto al = [](int x) { return (x + 15) & ~15; };
     int o = 0;
-    F.Kcap = Kcap; F.cmask = Ccap - 1; F.Tcap = Tcap; F.Ncap = Ncap;
+    Ncap = std::max(Ncap, Tcap);                           // the two-clade member lists (2 x Tcap ints) reuse g_score
+    F.Kcap = Kcap; F.Mcap = Mcap; F.cmask = Ccap - 1; F.Tcap = Tcap; F.Ncap = Ncap;
+    F.o_stat = o; o += al(8 * 8 + 8);                      // 8 counters + the level's clade count
     F.o_llo = o; o += al(4 * GMAX);
     F.o_llen = o; o += al(4 * GMAX);
     F.o_lraw = o; o += al(4 * GMAX);
     F.o_lstr = o; o += al(GMAX);
-    F.o_goff = o; o += al(2 * (GMAX + 2));
+    F.o_lbase = o; o += al(2 * (GMAX + 2));
     F.o_maxv = o; o += al(8 * GMAX);
     F.o_unk = o; o += al(8 * GMAX);
-    const int buf0 = o;
-    F.o_bv = o; o += al(8 * Kcap);
-    F.o_bab = o; o += al(4 * Kcap);
-    F.o_bt = o; o += al(2 * Kcap);
-    // survivors of the two-clade prefilter reuse [o_bv, o_bcl): 12 bytes each
-    F.Scap = ((o - buf0) / 12) & ~1;
-    F.o_bcl = o; o += al(4 * Kcap + 8);   // int clade ids, then u16 bord[Kcap] + u16 grs[Kcap + 2]
-    F.o_bh = o; o += annotations ? al(4 * Kcap) : 0;
-    F.o_hkey = o; o += al(4 * std::max(Ccap, 2 * Tcap));   // also the melded-member lists (2 x Tcap ints)
+    F.o_rhit = o; o += al(2 * Mcap);
+    F.o_rab = o; o += al(4 * Mcap);
+    // scratch: one-clade rank cache (Tcap doubles) | two-clade candidates (Tcap u16) + survivors (12 bytes each)
+    F.Scap = (Scap + 1) & ~1;
+    F.x_bytes = std::max(8 * Tcap, al(2 * Tcap) + 12 * F.Scap);
+    F.o_x = o; o += al(F.x_bytes);
+    const int lvl0 = o;
+    F.o_hkey = o; o += al(4 * Ccap);                       // also: one-clade member list, parents of the clades (Tcap ints)
     F.o_hval = o; o += al(2 * Ccap);                       // also memA / memB (2 x Tcap bytes)
     F.o_clid = o; o += al(4 * Tcap);
     F.o_mk0 = o; o += al(4 * Tcap);
     F.o_mk1 = o; o += al(4 * Tcap);
     F.o_mk2 = o; o += al(4 * Tcap);
-    F.o_cur = o; o += al(2 * (Tcap + 2));
+    F.o_clhead = o; o += al(2 * Tcap);
+    F.o_cltail = o; o += al(2 * Tcap);
     F.o_gscore = o; o += al(8 * Ncap);
+    F.o_gu = o; o += al(4 * Kcap);
     F.o_gt = o; o += al(2 * Ncap);
+    F.o_gnext = o; o += al(2 * Ncap);
+    F.o_gloc = o; o += al(Ncap);
+    o = std::max(o, lvl0 + al(14 * Kcap + 16));            // the per-locus sort of the prologue is staged from o_hkey on
+    F.Hcap = std::min(65535, (o - lvl0) / 8);              // as are the hits: u32 span + u32 locus mask each
     F.slice_bytes = o;
     return o;
 }

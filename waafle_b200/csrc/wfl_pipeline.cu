@@ -167,7 +167,8 @@ __device__ __noinline__ void write_result(const PipeArgs &a, long long c, const 
     int r_call = WFL_CALL_UNCLASSIFIED, r_dir = 0, r_c1 = -1, r_c2 = -1, r_lca = -1, r_b1 = -1, r_b2 = -1, \
         r_na = 0, r_nb = 0, r_status = 0;                                                           \
     long long r_mem = 0;                                                                            \
-    double r_crit = 0.0, r_rank = 0.0;
+    double r_crit = 0.0, r_rank = 0.0;                                                              \
+    (void)r_status;
 
 #define EMIT_RESULT(status_)                                                                        \
     do {                                                                                            \
@@ -231,8 +232,6 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
         const int H = (int)(a.b.hit_off[c + 1] - h0), Graw = (int)(a.b.locus_off[c + 1] - l0);
         RESULT_LOCALS
         bool bad_input = false, overflow = false;
-        unsigned long long need_hint = 0;
-        (void)need_hint;
         // region A
         const size_t capA = loci_bytes(Graw);
         unsigned long long offA = 0;
@@ -324,11 +323,6 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_prepare(const Pipe
                 M += tot;
             }
             __syncwarp();
-            // worst case for this contig (groups <= M + G, clades <= groups + 1): one replay suffices
-            need_hint = 96ull * Graw + 2ull * np_tot + 64ull * (unsigned long long)M +
-                        48ull * ((unsigned long long)M + G + 2) +
-                        (80ull + 24ull * W) * ((unsigned long long)M + G + 2) + 16ull * (2 * M + 64) +
-                        (unsigned long long)G * (64 + 16 * S) + (1ull << 12);
             // region B
             size_t persist = 0;
             const size_t capB = record_bytes(M, G, W, S, np_tot, (tax.n_nodes + 31) >> 5, &persist);
@@ -969,7 +963,6 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_masks
             __syncwarp();
             if (lane == 0) *Lp = Level{G, W, T, Ngrp, nun, g_loc, g_score, cl_id, cl_go, {mk0, mk1, mk2}, um, ign, l_len, cl_par};
             __syncwarp();
-            const Level &L = *Lp;
             cont_ok = true;
         }
         PH_END(4);
@@ -1120,8 +1113,6 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
         (void)nu; (void)t_unk; (void)hasroot; (void)spike; (void)T; (void)r_t; (void)r_loc;
         const Level &L = *Lp;
         bool overflow = false, undecided = false;
-        unsigned long long need_hint = 0;
-        (void)need_hint;
         long long n_ptest = 0, n_pscore = 0;
 #pragma unroll 1
         for (int once = 0; once < 1; ++once) {
@@ -1188,7 +1179,6 @@ __global__ void __launch_bounds__(32, WFL_PIPE_CPSM) wfl_pipe_two(const PipeArgs
             }
             if (nsurv > scap) {   // survivor list does not fit: replay with a slab sized for all pairs
                 overflow = true;
-                need_hint += 16ull * (unsigned long long)NP + 4096ull;
                 break;
             }
             n_pscore += nsurv;

@@ -563,48 +563,33 @@ __device__ __noinline__ double group_integral_general(const double *bv, const u3
     return sum;
 }
 
-// Closed-form envelope integral of a group with >= 2 records: pick records in descending score order (ties: buffer
-// order), keep the union of the picked intervals as ONE interval [ua, ub) and add v * (newly covered sites).  Stops as
-// soon as the union covers the hull of the group.  A picked interval that leaves a gap -> generic sweep.
-__device__ __forceinline__ double group_integral(const double *bv, const u32 *bab, const u16 *bord, int rs, int re) {
-    double vlast = 1e300;   // above any score
-    int qlast = -1, ua = 0, ub = 0, hull_a = 0x7fffffff, hull_b = 0;
-    double sum = 0.0;
+// Closed-form envelope integral of a group with >= 2 records that arrive in DESCENDING SCORE order (the fast path sorts
+// every locus' records once per contig; stable splits keep the order inside each group): the union of the records seen
+// so far is kept as ONE interval [ua, ub) and every record adds v * (newly covered sites).  A record that leaves a gap
+// sends the group to the generic sweep.  n = gene length: once the union covers the gene nothing can be added.
+__device__ __forceinline__ double group_integral(const double *bv, const u32 *bab, const u16 *bord, int rs, int re, int n) {
+    int r = bord[rs];
+    u32 ab = bab[r];
+    int ua = (int)(ab & 0xffffu), ub = (int)(ab >> 16);
+    double sum = bv[r] * (double)(ub - ua);
 #pragma unroll 1
-    for (int pick = 0;; ++pick) {
-        double bvv = -1.0;
-        int bq = -1;
-#pragma unroll 1
-        for (int q = rs; q < re; ++q) {
-            const int r = bord[q];
-            const double v = bv[r];
-            const bool el = v < vlast || (v == vlast && q > qlast);
-            if (el && v > bvv) { bvv = v; bq = q; }
-            if (pick == 0) {
-                const u32 ab = bab[r];
-                hull_a = min(hull_a, (int)(ab & 0xffffu));
-                hull_b = max(hull_b, (int)(ab >> 16));
-            }
-        }
-        if (bq < 0 || !(bvv > 0.0)) break;
-        const u32 ab = bab[bord[bq]];
+    for (int q = rs + 1; q < re; ++q) {
+        if (ua == 0 && ub == n) break;
+        r = bord[q];
+        const double v = bv[r];
+        if (!(v > 0.0)) break;   // descending: the rest contributes nothing
+        ab = bab[r];
         const int a = (int)(ab & 0xffffu), b = (int)(ab >> 16);
-        if (pick == 0) {
-            ua = a; ub = b;
-            sum = bvv * (double)(b - a);
-        } else {
-            if (a > ub || b < ua) return group_integral_general(bv, bab, bord, rs, re);
-            sum += bvv * (double)(max(0, ua - a) + max(0, b - ub));
+        if (a > ub || b < ua) return group_integral_general(bv, bab, bord, rs, re);
+        const int add = max(0, ua - a) + max(0, b - ub);
+        if (add) {
+            sum += v * (double)add;
             ua = min(ua, a);
             ub = max(ub, b);
         }
-        vlast = bvv;
-        qlast = bq;
-        if (ua <= hull_a && ub >= hull_b) break;
     }
     return sum;
 }
-
 // K2-HOST-END
 
 // Generic sequential pairwise sum for the short gene-level vectors of Contig.score.

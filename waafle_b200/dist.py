@@ -101,11 +101,9 @@ def gather_blobs(blob, dist, dst=0):
     return out, sizes
 
 
-def merge_blobs(blobs, hit_bases):
-    """Per-rank packed results (uint8 numpy arrays, rank order) -> the result arrays of the whole batch.
-    `hit_bases[r]` = index of rank r's first hit in the whole batch (annotation winners are batch hit indices)."""
-    from .engine import unpack_results
-    parts = [unpack_results(b) for b in blobs]
+def merge_results(parts, hit_bases):
+    """Result dicts of consecutive contig ranges -> the result arrays of the whole batch.
+    `hit_bases[r]` = index of part r's first hit in the whole batch (annotation winners are batch hit indices)."""
     out = {}
     for k in ("call", "direction", "lifts", "clade1", "clade2", "lca", "best1", "best2", "crit", "rank",
               "n_members_a", "members", "synteny", "locus_flags"):
@@ -123,6 +121,12 @@ def merge_blobs(blobs, hit_bases):
     out["call_counts"] = np.array([len(o) for o in order], dtype=np.int64)
     out["call_index"] = np.concatenate(order).astype(np.int64)
     return out
+
+
+def merge_blobs(blobs, hit_bases):
+    """Per-rank packed results (uint8 numpy arrays, rank order) -> the result arrays of the whole batch."""
+    from .engine import unpack_results
+    return merge_results([unpack_results(b) for b in blobs], hit_bases)
 
 
 def gather_results(res, hit_base, dist, device=None):

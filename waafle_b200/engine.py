@@ -26,7 +26,8 @@ EXPORTS = ["wfl_abi_version", "wfl_device_count", "wfl_create", "wfl_destroy", "
            "wfl_set_params", "wfl_set_taxonomy", "wfl_score_batch", "wfl_score_packed", "wfl_upload_batch",
            "wfl_upload_packed", "wfl_run_resident", "wfl_download_results", "wfl_get_stats", "wfl_set_option",
            "wfl_pack_results", "wfl_packed_results_layout", "wfl_debug_gene_scores", "wfl_host_alloc",
-           "wfl_host_free"]
+           "wfl_host_free", "wfl_parser_create", "wfl_parser_destroy", "wfl_parser_last_error", "wfl_parse_blast",
+           "wfl_parse_distinct", "wfl_parse_fetch", "wfl_parser_times"]
 ABI_VERSION = 2
 PACKED_MAX_NODES, PACKED_MAX_COORD, PACKED_MAX_SYSTEMS = 16384, 65535, 8
 
@@ -66,7 +67,9 @@ class CStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int64) for k in
                 ("kernel_launches", "contigs", "hits", "loci", "matched_pairs", "groups", "levels",
                  "pairs_tested", "pairs_scored", "workspace_retries", "smem_contigs", "fallback_contigs",
-                 "guard_trips", "refined_groups", "host_syncs")] + \
+                 "second_pass_contigs")] + \
+               [("fallback_reasons", ctypes.c_int64 * 8)] + \
+               [(k, ctypes.c_int64) for k in ("guard_trips", "refined_groups", "host_syncs")] + \
                [("phase_cycles", ctypes.c_int64 * 12)] + \
                [(k, ctypes.c_float) for k in ("ms_h2d", "ms_kernels", "ms_d2h", "ms_score_kernel")]
 
@@ -353,6 +356,7 @@ class Engine:
         self._check(self._lib.wfl_get_stats(self._h, ctypes.byref(s)))
         d = {k: getattr(s, k) for k, _ in CStats._fields_}
         d["phase_cycles"] = list(d["phase_cycles"])
+        d["fallback_reasons"] = list(d["fallback_reasons"])
         return d
 
     def debug_gene_scores(self, contig, capacity=1 << 16):

@@ -56,6 +56,8 @@ def get_args(argv=None):
     g.add_argument("--stranded", action="store_true")
     g = parser.add_argument_group("engine")
     g.add_argument("--device", type=int, default=0, help="CUDA device index [default: 0]")
+    g.add_argument("--cpu-parse", action="store_true",
+                   help="parse the blastout with the CPU reader instead of the CUDA parser")
     g.add_argument("--chunk-contigs", type=int, default=250000,
                    help="contigs per engine call (streaming; results are merged) [default: 250000]")
     return parser.parse_args(argv)
@@ -105,10 +107,10 @@ def main(argv=None):
     if args.basename is None:
         args.basename = os.path.split(args.contigs)[1].split(".")[0]
     say("Analyzing contigs.")
-    hits = parsers.read_blast_hits(args.blastout)
+    hits = parsers.read_blast_hits(args.blastout, device=None if args.cpu_parse else args.device)
     if hits.sysmask is None:
         die("more than 32 annotation systems in the subject headers")
-    tax.build(set(hits.taxon))
+    tax.build(hits.distinct_taxa())
     batch = packing.pack(contig_lengths, loci, hits, tax)
     params = OrgscorerParams.from_args(args, n_systems=len(hits.systems))
     engine = Engine(args.device, params, tax)

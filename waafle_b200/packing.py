@@ -70,6 +70,22 @@ class Batch:
             contig_lengths=cut(self.contig_lengths, c0, c1),
             hit_row=cut(self.hit_row, h0, h1), locus_row=cut(self.locus_row, l0, l1))
 
+    def sort_hits(self):
+        """The same batch with every contig's hits in descending waafle_score order (ties keep their order).  Semantically
+        transparent -- envelopes are order-free and the annotation tie-break "last hit in file order" (OS:389) is the
+        largest index among equal scores either way -- and it lets the fused fast-path kernel skip its per-locus sort."""
+        n = self.n_contigs
+        contig = np.repeat(np.arange(n, dtype=np.int64), np.diff(self.hit_off))
+        order = np.lexsort((np.arange(len(contig)), -self.hit_score, contig))
+        take = lambda a: None if a is None else np.ascontiguousarray(a[order])
+        return Batch(
+            hit_off=self.hit_off, locus_off=self.locus_off,
+            hit_qstart=take(self.hit_qstart), hit_qend=take(self.hit_qend), hit_taxon=take(self.hit_taxon),
+            hit_score=take(self.hit_score), hit_scov=take(self.hit_scov), hit_strand=take(self.hit_strand),
+            locus_start=self.locus_start, locus_end=self.locus_end, locus_strand=self.locus_strand,
+            hit_sysmask=take(self.hit_sysmask), contig_names=self.contig_names, contig_lengths=self.contig_lengths,
+            hit_row=take(self.hit_row), locus_row=self.locus_row)
+
     def can_pack(self, n_nodes, n_systems=0):
         """True if the compact wire format (wfl_packed_batch) can carry this batch."""
         hi = max(int(self.hit_qstart.max(initial=0)), int(self.hit_qend.max(initial=0)))
@@ -94,6 +110,44 @@ class Batch:
         """29 B/hit + 9 B/locus + 16 B/contig in, 40 + G(1+4S) B/contig out."""
         return (29 * self.n_hits + 9 * self.n_loci + 16 * self.n_contigs
                 + 40 * self.n_contigs + self.n_loci * (1 + 4 * n_systems))
+
+
+def concat_batches(parts):
+    """Concatenate batches (contigs of parts[0], then parts[1], ...) with rebased offsets."""
+    def cat(name):
+        arrs = [getattr(p, name) for p in parts]
+        return None if any(a is None for a in arrs) else np.concatenate(arrs)
+
+    def cat_off(name, total_name):
+        out, base = [np.zeros(1, np.int64)], 0
+        for p in parts:
+            o = getattr(p, name)
+            out.append(o[1:] + base)
+            base += int(o[-1])
+        return np.concatenate(out)
+
+    names = []
+    for p in parts:
+        names += list(p.contig_names)
+    return Batch(
+        hit_off=cat_off("hit_off", "n_hits"), locus_off=cat_off("locus_off", "n_loci"),
+        hit_qstart=cat("hit_qstart"), hit_qend=cat("hit_qend"), hit_taxon=cat("hit_taxon"),
+        hit_score=cat("hit_score"), hit_scov=cat("hit_scov"), hit_strand=cat("hit_strand"),
+        locus_start=cat("locus_start"), locus_end=cat("locus_end"), locus_strand=cat("locus_strand"),
+        hit_sysmask=cat("hit_sysmask"), contig_names=names, contig_lengths=cat("contig_lengths"))
+
+
+def tiled_slice(base, c0, c1):
+    """Contigs [c0, c1) of the infinite tiling base, base, base, ... (synthetic weak / strong scaling workloads)."""
+    n = base.n_contigs
+    parts = []
+    c = c0
+    while c < c1:
+        lo = c % n
+        hi = min(n, lo + (c1 - c))
+        parts.append(base.slice(lo, hi))
+        c += hi - lo
+    return concat_batches(parts) if len(parts) != 1 else parts[0]
 
 
 def _group(names, index, what, codes=None, code_names=None):
@@ -123,14 +177,24 @@ def pack(contig_lengths, loci, hits, taxonomy):
     locus_off = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(lc[lrow], minlength=n), out=locus_off[1:])
 
-    hc = _group(hits.qseqid, index, "blastout", getattr(hits, "qseqid_codes", None), getattr(hits, "qseqid_names", None))
-    if len(hc):
-        # the reference assumes the blastout is grouped by query (UT:255-258)
-        starts = np.r_[True, hits.qseqid[1:] != hits.qseqid[:-1]]
-        blocks = hc[starts]
-        blocks = blocks[blocks >= 0]
-        if len(np.unique(blocks)) != len(blocks):
+    if getattr(hits, "block_starts", None) is not None and len(hits):
+        # run-length coded query names (GPU parser): one lookup per block, no per-row objects
+        bcid = np.fromiter((index.get(nm, -1) for nm in hits.block_names), dtype=np.int64, count=len(hits.block_names))
+        for nm in np.array(hits.block_names, dtype=object)[bcid < 0]:
+            say("  Unknown contig in <{}> file".format("blastout"), nm)
+        known = bcid[bcid >= 0]
+        if len(np.unique(known)) != len(known):   # the reference assumes the blastout is grouped by query (UT:255-258)
             die("blastout is not grouped by query sequence")
+        hc = np.repeat(bcid, np.diff(np.r_[hits.block_starts, len(hits)]))
+    else:
+        hc = _group(hits.qseqid, index, "blastout", getattr(hits, "qseqid_codes", None), getattr(hits, "qseqid_names", None))
+        if len(hc):
+            # the reference assumes the blastout is grouped by query (UT:255-258)
+            starts = np.r_[True, hits.qseqid[1:] != hits.qseqid[:-1]]
+            blocks = hc[starts]
+            blocks = blocks[blocks >= 0]
+            if len(np.unique(blocks)) != len(blocks):
+                die("blastout is not grouped by query sequence")
     hrow = np.nonzero(hc >= 0)[0]
     hrow = hrow[np.argsort(hc[hrow], kind="stable")]
     hit_off = np.zeros(n + 1, dtype=np.int64)
@@ -157,4 +221,4 @@ def pack(contig_lengths, loci, hits, taxonomy):
         locus_strand=np.ascontiguousarray(loci.strand[lrow]),
         contig_names=names,
         contig_lengths=np.array([contig_lengths[k] for k in names], dtype=np.int64),
-        hit_row=hrow, locus_row=lrow)
+        hit_row=hrow, locus_row=lrow).sort_hits()

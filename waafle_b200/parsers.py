@@ -39,11 +39,12 @@ class HitTable:
 
     def __init__(self, qseqid, qstart, qend, taxon, score, scov_modified, strand,
                  sseqid_id, sseqid_names, sseqid_annotations, systems, sysmask,
-                 taxon_codes=None, taxon_names=None, qseqid_codes=None, qseqid_names=None):
-        self.qseqid = qseqid                # object array of contig names
+                 taxon_codes=None, taxon_names=None, qseqid_codes=None, qseqid_names=None,
+                 block_starts=None, block_names=None):
+        self._qseqid = qseqid               # object array of contig names (None: see block_starts)
         self.qstart = qstart                # int32
         self.qend = qend                    # int32
-        self.taxon = taxon                  # object array of taxon names (sseqid field 1)
+        self._taxon = taxon                 # object array of taxon names (sseqid field 1; None: see taxon_codes)
         self.score = score                  # float64  waafle_score      UT:229
         self.scov_modified = scov_modified  # float64                    UT:227
         self.strand = strand                # int8 '+' / '-'             UT:214
@@ -56,9 +57,29 @@ class HitTable:
         # few distinct names once instead of looking every row up
         self.taxon_codes, self.taxon_names = taxon_codes, taxon_names
         self.qseqid_codes, self.qseqid_names = qseqid_codes, qseqid_names
+        # run-length view of `qseqid` (GPU parser): rows block_starts[b] .. block_starts[b+1] share block_names[b]
+        self.block_starts, self.block_names = block_starts, block_names
 
     def __len__(self):
         return len(self.qstart)
+
+    @property
+    def qseqid(self):
+        if self._qseqid is None and self.block_starts is not None:
+            lens = np.diff(np.r_[self.block_starts, len(self)])
+            self._qseqid = np.repeat(np.array(self.block_names, dtype=object), lens)
+        return self._qseqid
+
+    @property
+    def taxon(self):
+        if self._taxon is None and self.taxon_codes is not None:
+            self._taxon = (np.array(self.taxon_names, dtype=object)[self.taxon_codes] if len(self.taxon_codes)
+                           else np.array([], dtype=object))
+        return self._taxon
+
+    def distinct_taxa(self):
+        """The taxon names seen in the hits (what Taxonomy.build needs), without a per-row object array."""
+        return set(self.taxon_names) if self.taxon_names is not None else set(self.taxon)
 
 
 def hits_from_columns(qseqid, sseqid, qlen, slen, qstart, qend, sstart, send, pident, sstrand):
@@ -229,8 +250,21 @@ def _parse_subject_headers_arrow(sseqid):
             tcodes_u[inv] if len(inv) else None, tnames)
 
 
-def read_blast_hits(path):
-    """Parse a waafle_search blastout file (15-field outfmt 6, UT:167-186)."""
+def read_blast_hits(path, device=None):
+    """Parse a waafle_search blastout file (15-field outfmt 6, UT:167-186).  With `device` (a CUDA device index) the rows
+    are parsed on the GPU (gpu_parse.BlastParser); files it cannot reproduce exactly fall through to the CPU reader."""
+    if device is not None:
+        from . import gpu_parse
+        with try_open(path) as fh:
+            text = fh.buffer.read() if hasattr(fh, "buffer") else fh.read().encode()
+        parser = gpu_parse.BlastParser(device)
+        try:
+            hits = parser.parse(text)
+        finally:
+            parser.close()
+        if hits is not None:
+            hits.parse_times = parser.times
+            return hits
     want = ("qseqid", "sseqid", "qlen", "slen", "qstart", "qend", "sstart", "send", "pident", "sstrand")
     cols, ok, text = None, False, None
     if pacsv is not None:

@@ -49,7 +49,8 @@ def _winner_annotations(batch, hits, res, systems):
     jj, ss = np.nonzero(aw >= 0)
     if len(jj) == 0:
         return {}
-    sid = np.asarray(hits.sseqid_id)[np.asarray(batch.hit_row)[aw[jj, ss]]]
+    rows = np.asarray(batch.hit_row)[aw[jj, ss]]
+    sid = rows if hits.sseqid_id is None else np.asarray(hits.sseqid_id)[rows]   # None: one header per row (GPU parser)
     uniq = np.unique(sid)
     parsed = {int(u): hits.sseqid_annotations[int(u)] for u in uniq}
     return {(int(j), int(s)): parsed[int(i)][systems[int(s)]] for j, s, i in zip(jj.tolist(), ss.tolist(), sid.tolist())}
