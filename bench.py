@@ -319,6 +319,11 @@ class E2E:
         return wdist.merge_blobs([g[r, :self.sizes[r]] for r in range(len(self.sizes))], hit_bases)
 
     def close(self):
+        # the pinned staging tensor was used on the engine's stream: hand it back to torch's host allocator while that
+        # stream still exists (the allocator records an event on it)
+        self.host_buf = None
+        if self.dist is not None:
+            self.torch.cuda.synchronize()
         self.eng.use_pinned_results(False)
         self.pin.close()
 

@@ -276,7 +276,9 @@ def test_fast_path_capacity_fallbacks():
         eng.close()
         assert not helpers.compare_results(ref, got, score_rtol=SCORE_RTOL), opts
         assert st["smem_contigs"] + st["fallback_contigs"] == batch.n_contigs
-        if opts:
+        if opts:   # overflows of the first pass go to the second one (3x the slice), what that cannot hold to the exact pipeline
+            assert st["second_pass_contigs"] > 0, opts
+        if "fast_tcap" in opts:
             assert st["fallback_contigs"] > 0, opts
 
 

@@ -110,8 +110,8 @@ def merge_results(parts, hit_bases):
         out[k] = np.concatenate([p[k] for p in parts])
     S = parts[0]["ann_winner"].shape[1]
     out["ann_winner"] = np.concatenate(
-        [np.where(p["ann_winner"] >= 0, p["ann_winner"] + int(hb), -1).astype(np.int32)
-         for p, hb in zip(parts, hit_bases)]).reshape(-1, S)
+        [np.where(p["ann_winner"] >= 0, p["ann_winner"] + int(hb), -1).astype(np.int32).reshape(-1)
+         for p, hb in zip(parts, hit_bases)]).reshape(len(out["synteny"]), S)
     moffs, base = [np.zeros(1, np.int64)], 0
     for p in parts:
         moffs.append(p["member_off"][1:] + base)
