@@ -43,7 +43,8 @@ struct wfl_engine {
     bool packed = false;                 // the resident batch is in the compact wire format
     // options (wfl_set_option / environment)
     bool exact = false;                  // every contig through the exact pipeline
-    int fast_kcap = 0, fast_mcap = 0, fast_tcap = 0, fast_ncap = 0;
+    int fast_hcap = 0, fast_mcap = 0, fast_tcap = 0, fast_ncap = 0;   // slice capacities of the fast kernel (0 = from the batch)
+    double fast_hscale = 1.6;            // first-pass hit capacity as a multiple of the mean hits per contig
     int fast_passes = 2;                 // 1: no second pass with a larger slice
     size_t pipe_pool_bytes = size_t(8192) << 20;
     size_t k2_cap_override = 0;
@@ -513,37 +514,34 @@ int run_pipeline_list(wfl_engine *e, DevCounters *ctr, const std::vector<int> &l
 // Capacities of the fast kernel's shared-memory slices, chosen from the shape of the batch (options override).
 // First pass: sized for the bulk of the contigs (hits per contig up to ~1.6x the mean), so that as many warps as possible
 // are resident; second pass: the contigs that overflowed, with a slice ~3x as large.
-static void fit_layout(wfl_engine *e, FastCfg &F, int K, int M, int T, int N, int Sc) {
+static void fit_layout(wfl_engine *e, FastCfg &F, int H, int M, int T, int N, int Sc) {
     for (;;) {
-        int C = 64;
-        while (C * 3 < T * 4) C <<= 1;   // load factor <= 0.75
-        fast_layout(F, K, M, C, T, N, Sc);
+        fast_layout(F, H, M, T, N, Sc, e->P.p.n_systems);
         if ((size_t)fast_warps_per_cta() * F.slice_bytes + 1024 <= e->smem_optin) break;
         // does not fit one CTA: shrink the largest consumers
         if (N > 96) N = std::max(96, N * 3 / 4);
         if (T > 64) T = std::max(64, T * 3 / 4);
         if (M > 128) M = std::max(128, M * 3 / 4);
-        if (K > 64) K = std::max(64, K * 3 / 4);
+        if (H > 128) H = std::max(128, H * 3 / 4);
         if (Sc > 64) Sc = std::max(64, Sc / 2);
-        if (N <= 96 && T <= 64 && M <= 128 && K <= 64) break;
+        if (N <= 96 && T <= 64 && M <= 128 && H <= 128) break;
     }
 }
 
 void choose_fast_cfg(wfl_engine *e) {
     int64_t hmax = 0;
     for (int64_t c = 0; c < e->n; ++c) hmax = std::max(hmax, e->h_hit_off[c + 1] - e->h_hit_off[c]);
-    const int64_t key[4] = {e->nh, e->nl, e->n * 2 + (e->packed ? 1 : 0), hmax};
+    const int64_t key[4] = {e->nh, e->nl, e->n * 2 + (e->packed ? 1 : 0), hmax * 64 + e->P.p.n_systems};
     if (!memcmp(key, e->cfg_key, sizeof key)) return;
     const double hbar = e->n > 0 ? (double)e->nh / (double)e->n : 0.0;        // hits per contig
-    const double kbar = e->nl > 0 ? (double)e->nh / (double)e->nl : 0.0;      // hits per locus
     auto r16 = [](double x) { return (int)((x + 15.0) / 16.0) * 16; };
-    const double hq = std::min((double)hmax, 1.6 * hbar);
-    const int K = e->fast_kcap ? e->fast_kcap : std::min(2048, std::max(64, r16(1.8 * kbar + 24)));
-    const int M = e->fast_mcap ? e->fast_mcap : std::min(16384, std::max(128, r16(hq + 16)));
-    const int T = e->fast_tcap ? e->fast_tcap : std::min(4096, std::max(64, r16(0.42 * hq + 16)));
-    const int N = e->fast_ncap ? e->fast_ncap : std::min(16384, std::max(96, r16(0.6 * hq + 32)));
-    fit_layout(e, e->fcfg, (K + 1) & ~1, M, T, N, 64);
-    fit_layout(e, e->fcfg2, (3 * K + 1) & ~1, 3 * M, 3 * T, 3 * N, 2048);
+    const double hq = std::min((double)hmax, e->fast_hscale * hbar);
+    const int H = e->fast_hcap ? e->fast_hcap : std::min(16384, std::max(64, r16(hq + 16)));
+    const int M = e->fast_mcap ? e->fast_mcap : std::min(16384, std::max(128, r16(1.06 * H + 16)));
+    const int T = e->fast_tcap ? e->fast_tcap : std::min(4096, std::max(64, r16(0.42 * H + 16)));
+    const int N = e->fast_ncap ? e->fast_ncap : std::min(16384, std::max(96, r16(0.6 * H + 32)));
+    fit_layout(e, e->fcfg, H, M, T, N, 64);
+    fit_layout(e, e->fcfg2, 3 * H, 3 * M, 3 * T, 3 * N, 2048);
     e->fast_grid = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfg, e->packed, 0));
     e->fast_grid2 = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfg2, e->packed, 0));
     memcpy(e->cfg_key, key, sizeof key);
@@ -649,7 +647,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         char *fs;
         if ((rc = outbuf(e, e->fb_list, 2 * ((size_t)e->n + 1), &fb_list))) return rc;
         if ((rc = outbuf(e, e->fast_wq, 256, &fwq))) return rc;
-        if ((rc = outbuf(e, e->fast_scratch, (size_t)std::max(e->fast_grid, e->fast_grid2) * fast_warps_per_cta() * e->fcfg2.Kcap * 16, &fs))) return rc;
+        if ((rc = outbuf(e, e->fast_scratch, std::max((size_t)e->fast_grid * e->fcfg.scratch_bytes, (size_t)e->fast_grid2 * e->fcfg2.scratch_bytes) * fast_warps_per_cta(), &fs))) return rc;
         CU(cudaMemsetAsync(fwq, 0, 256 * sizeof(unsigned long long), e->stream));
     }
     CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
@@ -983,7 +981,8 @@ int wfl_set_option(wfl_engine *e, const char *name, int64_t value) {
     if (!e || !name) return WFL_ERR_ARG;
     const std::string k(name);
     if (k == "exact") e->exact = value != 0;
-    else if (k == "fast_kcap") e->fast_kcap = (int)std::max<int64_t>(0, value);
+    else if (k == "fast_kcap" || k == "fast_hcap") e->fast_hcap = (int)std::max<int64_t>(0, value);
+    else if (k == "fast_hscale_pct") e->fast_hscale = std::max<int64_t>(50, value) / 100.0;
     else if (k == "fast_mcap") e->fast_mcap = (int)std::max<int64_t>(0, value);
     else if (k == "fast_tcap") e->fast_tcap = (int)std::max<int64_t>(0, value);
     else if (k == "fast_passes") e->fast_passes = value >= 2 ? 2 : 1;
@@ -1022,7 +1021,8 @@ int wfl_create(int device, wfl_engine **out) {
     if (const char *k = getenv("WFL_POOL_MB")) e->pipe_pool_bytes = (size_t)atoll(k) << 20;
     if (const char *k = getenv("WFL_CHUNK_MB")) { e->chunk_bytes = (size_t)std::max<long long>(1, atoll(k)) << 20; e->chunk_fixed = true; }
     if (const char *k = getenv("WFL_STREAMS")) e->n_slots = atoi(k) >= 2 ? 2 : 1;
-    if (const char *k = getenv("WFL_FAST_KCAP")) e->fast_kcap = atoi(k);
+    if (const char *k = getenv("WFL_FAST_HCAP")) e->fast_hcap = atoi(k);
+    if (const char *k = getenv("WFL_FAST_HSCALE")) e->fast_hscale = std::max(0.5, atof(k));
     if (const char *k = getenv("WFL_FAST_TCAP")) e->fast_tcap = atoi(k);
     if (const char *k = getenv("WFL_FAST_NCAP")) e->fast_ncap = atoi(k);
     for (auto &ev : e->ev)

@@ -83,17 +83,19 @@ struct PlanEntry {
 // Layout of one warp's shared-memory slice (byte offsets) and its capacities; computed on the host.
 struct FastCfg {
     int slice_bytes;
-    int Hcap;      // hits of one contig (staging of the spans)
+    int Hcap;      // staged entries of one contig: one per (hit, locus) match == record; hits matching no locus are dropped
+    int Pcap;      // power of two >= Hcap: the permutation of the per-level hit sort
     int Mcap;      // records (hit x locus matches) of one contig
-    int Kcap;      // records of one locus
-    int cmask;     // clade hash slots - 1 (power of two)
     int Tcap;      // distinct clades per level
     int Ncap;      // (clade, locus) groups per level
     int Scap;      // two-clade pairs that pass the mask prefilter
-    int x_bytes;   // scratch area
-    int o_stat, o_llo, o_llen, o_lraw, o_lstr, o_lbase, o_maxv, o_unk;
-    int o_rhit, o_rab, o_x;
-    int o_hkey, o_hval, o_clid, o_mk0, o_mk1, o_mk2, o_clhead, o_cltail, o_gscore, o_gu, o_gt, o_gnext, o_gloc;
+    int x_bytes;   // search scratch (aliases the per-level record / group arrays, dead by then)
+    int scratch_bytes;   // global scratch per resident warp: locus masks of the staged hits + cold-path record arrays
+    int o_stat, o_llo, o_llen, o_lraw, o_lstr, o_lbase, o_lcur, o_llast, o_maxb, o_unk;
+    int o_hv, o_hsp, o_hcl, o_hid, o_hloc;
+    int o_rec, o_gstart, o_gt, o_gloc, o_x;
+    int o_row;     // gene scores in clade-major CSR order; the sort permutation (u16[Pcap]) lives here until they are written
+    int o_clid, o_mk0, o_mk1, o_mk2, o_pres, o_cstart;
 };
 
 struct FastArgs {
@@ -117,9 +119,9 @@ struct FastArgs {
     int plan_nmax;
     const PlanEntry *plan_index;
     const uint16_t *plan_data;
-    char *scratch;                 // 16 * Kcap bytes per resident warp (exact recomputation of near-threshold groups)
+    char *scratch;                 // cfg.scratch_bytes per resident warp
 };
-int fast_layout(FastCfg &F, int Kcap, int Mcap, int Ccap, int Tcap, int Ncap, int Scap);
+int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, int n_systems);
 int fast_warps_per_cta();
 int fast_ctas_per_sm(const FastCfg &F, bool packed, size_t smem_per_sm);
 cudaError_t launch_fast(const FastArgs &a, bool packed, int grid, cudaStream_t s);

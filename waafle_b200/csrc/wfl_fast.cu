@@ -8,15 +8,21 @@
 // LGT checks :678-744.
 //
 // How it works (and differs from the exact pipeline, wfl_pipeline.cu):
-//  * once per contig: the hit spans are staged in shared memory, one pass per locus appends the attached hits
-//    (records: hit index + python slice, locus-major), and every locus' records are put in DESCENDING SCORE order
-//    (skipped when they already are: the front end's packer delivers hits sorted by score);
-//  * per taxonomy level, per locus: the records are streamed in score order; each record's clade (the level's row of
-//    the ancestor table: a lift re-bins the site arrays by parent, waafle_orgscorer.py:431-445) gets a dense handle
-//    from a shared-memory hash, and the clade's running ENVELOPE STATE for this locus -- the union of its better hits
-//    as one interval and sum v * (newly covered sites) -- is updated in place.  That sum / n is the closed form of
-//    np.mean of the site array (:371-382, :399-406); no grouping sort, no per-group scan.  A hit that leaves a gap
-//    marks the group for a generic endpoint sweep;
+//  * once per contig, ONE coalesced pass over the contig's hit columns: every hit is tested against the loci
+//    (attach_hits); the hits attached to at least one locus are STAGED in shared memory (score, span, clade) together
+//    with the mask of their loci -- hits attached to nothing never reach the site arrays and are dropped here;
+//  * per taxonomy level the staged hits are visited in (clade ascending, score descending) order.  The front end's
+//    packer delivers every contig's hits in exactly that order for level 0 (packing.Batch.sort_hits), so the order is
+//    only CHECKED there; after a lift (clade := parent, raise_taxonomy :431-445) or for unsorted input a bitonic sort of
+//    the hit permutation restores it.  In that order
+//      - the distinct clades of the level are the runs of equal clade: dense handles in ascending node index == name
+//        order, no hash table;
+//      - one pass emits the records (hit x locus) locus-major, so the records of a (clade, locus) group are adjacent
+//        and descending in score;
+//  * gene scores, one LANE per (clade, locus) group: the group's records are streamed in score order while the union of
+//    the better hits is kept as one interval [ua, ub): every record adds score x (newly covered sites).  That sum / n is
+//    the closed form of np.mean of the site array (:371-382, :399-406).  A record that leaves a gap sends the group to
+//    a generic endpoint sweep (cold);
 //  * numpy's pairwise rounding is not reproduced, so the value is within ~1e-14 of np.mean; instead every DECISION
 //    is protected by a guard band:
 //      - a gene score within 1e-12 of a threshold it is compared with (k1, k2, 1e-6) is recomputed exactly, in
@@ -24,10 +30,10 @@
 //      - a rank within 1e-12 of the best rank (arg-max) or of best - range (meld set) cannot be settled locally:
 //        the contig is handed to the exact pipeline;
 //    so calls / clades / synteny are bit-exact and crit / rank agree to <= 1e-12 (north_star tolerance);
-//  * gene-score rows are per-clade linked lists of (locus, score) in locus order; every tie-break the reference
-//    resolves by name order uses the node index explicitly (handles are arbitrary labels).
-// Anything the slice cannot hold (too many loci / records / clades / groups / pairs) is retried by a second launch
-// with a larger slice; long genes, > 32 loci, --min-overlap <= 0, guard-band trips and malformed input go to the
+//  * gene-score rows are a clade-major CSR addressed through each clade's locus-presence bitmask: row(t, i) is one
+//    popc away, no list walks.
+// Anything the slice cannot hold (too many attached hits / records / clades / groups / pairs) is retried by a second
+// launch with a larger slice; long genes, > 32 loci, --min-overlap <= 0, guard-band trips and malformed input go to the
 // exact pipeline.
 #include "wfl_warp_common.cuh"
 
@@ -36,19 +42,13 @@ namespace wfl {
 namespace {
 
 constexpr int FAST_WPC = 4;     // warps (= contigs in flight) per CTA
-constexpr int EMPTY_KEY = -1;
 constexpr int GMAX = 32;        // retained loci per contig: gene bitmasks are one 32-bit word
 constexpr int NONE16 = 0xffff;
 #ifndef WFL_FAST_CPSM
-#define WFL_FAST_CPSM 4         // resident CTAs per SM the kernel is compiled for (register budget)
+#define WFL_FAST_CPSM 5         // resident CTAs per SM the kernel is compiled for (register budget)
 #endif
 
 #define SM(T, off) (reinterpret_cast<T *>(slice + (off)))
-
-__device__ __forceinline__ u32 hash32(int key) {
-    u32 x = (u32)key * 2654435761u;
-    return x ^ (x >> 15);
-}
 
 // hit x locus test (waafle_orgscorer.py:365-367, utils.py:487-500) for OVERLAPPING intervals and min_overlap > 0.
 // The quotient is only formed when the comparison is within 2^-40 of the threshold (fl is monotone, so outside
@@ -67,10 +67,9 @@ struct FLevel {
     int G, T, t_unk;         // t_unk: handle of the spiked Unknown (dense row unk_row), -1 if none
     u32 um;                  // non-ignored loci
     int nun;
-    const u16 *cl_head;      // first group of each clade; groups of a clade are linked in locus order
-    const u16 *g_next;
-    const u8 *g_loc;
-    const double *g_score;
+    const u32 *pres;         // loci in which the clade has a gene score
+    const u16 *cstart;       // first entry of the clade's row in `row` (entries in locus order)
+    const double *row;
     const double *unk_row;
     const int *cl_id;
     const u32 *mk[3];        // per clade gene bitmasks: score >= k1 / k2 / 1e-6
@@ -78,21 +77,12 @@ struct FLevel {
     const int *cl_par;       // two-clade search with sister penalty: parent of every LISTED clade of the level, else -1
 };
 
-// gene-score row of one clade, walked in locus order (0 where the clade has no entry, waafle_orgscorer.py:404-405)
-struct RowWalk {
-    int p;
-    bool dense;
-    __device__ __forceinline__ void open(const FLevel &L, int t) {
-        dense = t == L.t_unk;
-        p = dense ? NONE16 : (int)L.cl_head[t];
-    }
-    __device__ __forceinline__ double at(const FLevel &L, int i) {
-        if (dense) return L.unk_row[i];
-#pragma unroll 1
-        while (p != NONE16 && (int)L.g_loc[p] < i) p = L.g_next[p];
-        return (p != NONE16 && (int)L.g_loc[p] == i) ? L.g_score[p] : 0.0;
-    }
-};
+// gene score of clade t at locus i (0 where the clade has no entry, waafle_orgscorer.py:404-405)
+__device__ __forceinline__ double row_at(const FLevel &L, int t, int i) {
+    if (t == L.t_unk) return L.unk_row[i];
+    const u32 p = L.pres[t];
+    return ((p >> i) & 1u) ? L.row[(int)L.cstart[t] + __popc(p & ((1u << i) - 1u))] : 0.0;
+}
 
 // Contig.score (waafle_orgscorer.py:447-461) over the non-ignored loci: crit = min, rank = np.mean (n <= 32 values:
 // numpy sums n < 8 sequentially, otherwise eight strided accumulators, the fixed tree, then the tail).
@@ -103,15 +93,12 @@ __device__ __noinline__ double row_stats(const FLevel &L, int t1, int t2, double
     u32 bits = L.um;
     const int body = n < 8 ? 0 : (n & ~7);
     int idx = 0;
-    RowWalk w1, w2;
-    w1.open(L, t1);
-    w2.open(L, t2 >= 0 ? t2 : t1);
 #pragma unroll 1
     while (bits) {
         const int i = __ffs(bits) - 1;
         bits &= bits - 1;
-        double v = w1.at(L, i);
-        if (t2 >= 0) v = fmax(v, w2.at(L, i));
+        double v = row_at(L, t1, i);
+        if (t2 >= 0) v = fmax(v, row_at(L, t2, i));
         crit = fmin(crit, v);
         if (idx < body) {
             const int j = idx & 7;
@@ -196,61 +183,30 @@ __device__ __noinline__ void eval_two_fast(const FLevel &L, const DevTax &tax, c
     ev.ok = ok;
 }
 
-// Dense handle of a clade in the level's shared-memory hash (get-or-insert).  Handles are arbitrary labels (insertion
-// order of a race); nothing downstream depends on their order.  All lanes call it (inactive lanes pass active = false).
-__device__ __forceinline__ int clade_handle(int *hkey, u16 *hval, int *cl_id, u32 *mk0, u32 *mk1, u32 *mk2, u16 *cl_head,
-                                            u16 *cl_tail, int *t_count, int cmask, int Tcap, u32 i0, u32 i1, u32 i2, int key,
-                                            bool active, bool &ovf) {
-    u32 slot = hash32(key) & (u32)cmask;
-    bool fail = false;
-    if (active) {
-        int probe = 0;
-#pragma unroll 1
-        for (; probe <= cmask; ++probe) {
-            const int old = atomicCAS(&hkey[slot], EMPTY_KEY, key);
-            if (old == EMPTY_KEY) {   // inserted: new clade of this level
-                const int hnew = atomicAdd(t_count, 1);
-                if (hnew < Tcap) {
-                    cl_id[hnew] = key;
-                    mk0[hnew] = i0; mk1[hnew] = i1; mk2[hnew] = i2;
-                    cl_head[hnew] = cl_tail[hnew] = (u16)NONE16;
-                    hval[slot] = (u16)hnew;
-                } else {
-                    hval[slot] = 0;
-                    fail = true;
-                }
-                break;
-            }
-            if (old == key) break;
-            slot = (slot + 1) & (u32)cmask;
-        }
-        if (probe > cmask) fail = true;
-        if (fail) ovf = true;
-    }
-    __syncwarp();
-    return (active && !fail) ? (int)hval[slot] : 0;
+// python slice [h1 : h2+1] of the locus' site array covered by a hit (waafle_orgscorer.py:373-382), for overlapping
+// intervals: a | b << 16
+__device__ __forceinline__ void hit_slice(u32 span, int lmin, int llen, int &a, int &b) {
+    a = max(0, (int)(span & 0xffffu) - lmin);
+    b = min(llen - 1, (int)(span >> 16) - lmin) + 1;
 }
 
-// Generic envelope integral of one (clade, locus) group whose better hits leave a gap: the group's records are the records
-// [r0, r0 + k) of the locus whose clade of this level is `clade`; they are gathered into the warp's global scratch (slices and
-// scores) and swept over their distinct endpoints.  Also serves the exact recomputation (numpy pairwise order) of a score
-// that falls inside the guard band.  Cold.
-template <class H>
-__device__ __noinline__ double group_slow(const FastArgs &a, const H &hits, char *scratch, int Kcap, const u16 *rec_hit,
-                                          const u32 *rec_ab, long long h0, int r0, int k, const int *anc, int clade, int n,
-                                          bool exact) {
-    int *ra = reinterpret_cast<int *>(scratch), *rb = ra + Kcap;
-    double *rv = reinterpret_cast<double *>(rb + Kcap);
+// Cold paths of one (clade, locus) group whose records are rec[r0 ...] while their clade is `clade` (and < lend): they are
+// gathered into the warp's global scratch (slices and scores, descending score order) and either swept over their distinct
+// endpoints (a better hit left a gap) or -- `exact`, for a score inside the guard band -- summed in numpy's pairwise order.
+__device__ __noinline__ double group_slow(const FastArgs &a, char *scratch, int cap, const u16 *rec, const u32 *hsp, const int *hcl,
+                                          const double *hv, int r0, int lend, int clade, int lmin, int n, bool exact) {
+    int *ra = reinterpret_cast<int *>(scratch), *rb = ra + cap;
+    double *rv = reinterpret_cast<double *>(rb + cap);
     int m = 0;
 #pragma unroll 1
-    for (int j = 0; j < k && m < Kcap; ++j) {
-        const long long h = h0 + rec_hit[r0 + j];
-        if (anc[hits.taxon(h)] != clade) continue;
-        const u32 ab = rec_ab[r0 + j];
-        const double sc = a.b.hit_score[h];
-        ra[m] = (int)(ab & 0xffffu);
-        rb[m] = (int)(ab >> 16);
-        rv[m] = sc > 0.0 ? sc : 0.0;
+    for (int q = r0; q < lend && m < cap; ++q) {
+        const int h = rec[q];
+        if (hcl[h] != clade) break;
+        int s, e;
+        hit_slice(hsp[h], lmin, n, s, e);
+        ra[m] = s;
+        rb[m] = e;
+        rv[m] = hv[h];
         ++m;
     }
     if (exact) {
@@ -277,16 +233,14 @@ __device__ __noinline__ double group_slow(const FastArgs &a, const H &hits, char
     return sum / (double)n;
 }
 
-// ascending node index order for the melded member lists (the exact pipeline emits them in handle == name order)
-__device__ __forceinline__ void emit_members_sorted(const FastArgs &a, const int *list, int n, long long dst, int lane) {
-#pragma unroll 1
-    for (int j = lane; j < n; j += 32) {
-        const int id = list[j];
-        int pos = 0;
-#pragma unroll 1
-        for (int q = 0; q < n; ++q) pos += list[q] < id;
-        if (dst + pos < a.o.mem_pool_cap) a.o.mem_pool[dst + pos] = id;
-    }
+// (clade ascending, score descending, staged index ascending) order of two staged hits; NONE16 pads sort last
+__device__ __forceinline__ bool hit_after(const int *hcl, const double *hv, int x, int y) {
+    if (x == NONE16 || y == NONE16) return x == NONE16 && y != NONE16;
+    const int cx = hcl[x], cy = hcl[y];
+    if (cx != cy) return cx > cy;
+    const double vx = hv[x], vy = hv[y];
+    if (vx != vy) return vx < vy;
+    return x > y;
 }
 
 struct FOut {
@@ -355,32 +309,35 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
     const Hits<PACKED> hits{a.b, P.p.min_scov};
     const double GUARD = a.guard;
     const double thr3[3] = {P.p.k1, P.p.k2, 1e-6};
+    const u32 le_mask = lt_mask() | (1u << lane);
 
+    // loci
     int *l_lo = SM(int, F.o_llo), *l_len = SM(int, F.o_llen), *l_raw = SM(int, F.o_lraw);
     signed char *l_str = SM(signed char, F.o_lstr);
-    u16 *l_base = SM(u16, F.o_lbase);
-    double *maxv = SM(double, F.o_maxv), *unk_row = SM(double, F.o_unk);
-    // level-invariant records (hit x locus matches), locus-major, descending score inside a locus: hit index and python
-    // slice [a, b) packed a | b << 16
-    u16 *rec_hit = SM(u16, F.o_rhit);
-    u32 *rec_ab = SM(u32, F.o_rab);
-    char *xs = SM(char, F.o_x);           // scratch: rank cache / two-clade candidates + survivors
-    // staging of the contig's hit spans / flags while the records are bucketed (aliases the per-level arrays)
-    u32 *hsp = SM(u32, F.o_hkey);
-    u32 *hmk = hsp + F.Hcap;              // loci each hit is attached to
-    // per-level arrays: clade hash and table, (clade, locus) groups
-    int *hkey = SM(int, F.o_hkey);
-    u16 *hval = SM(u16, F.o_hval);
+    u16 *l_base = SM(u16, F.o_lbase);            // records of locus i: rec[l_base[i] .. l_base[i + 1])
+    u16 *l_cur = SM(u16, F.o_lcur);              // emission cursor / record count of the locus
+    u16 *l_last = SM(u16, F.o_llast);            // clade handle of the locus' last emitted record
+    u64 *maxb = SM(u64, F.o_maxb);               // per-locus max gene score (order-preserving bits)
+    double *unk_row = SM(double, F.o_unk);
+    // staged (attached) hits, level-invariant but for the clade
+    double *hv = SM(double, F.o_hv);             // waafle score, clamped at 0 (sites start at 0, np.zeros :381)
+    u32 *hsp = SM(u32, F.o_hsp);                 // span on the contig: min | max << 16
+    int *hcl = SM(int, F.o_hcl);                 // clade of the hit at the current level
+    u16 *hid = SM(u16, F.o_hid);                 // index of the hit in the contig (annotation winners; only with systems)
+    u8 *hloc = SM(u8, F.o_hloc);                 // locus of the entry
+    // per level
+    u16 *rec = SM(u16, F.o_rec);                 // records (staged hit index), locus-major, (clade, score desc) inside
+    u16 *gstart = SM(u16, F.o_gstart), *g_t = SM(u16, F.o_gt);   // (clade, locus) groups: first record, clade handle
+    u8 *g_loc = SM(u8, F.o_gloc);
+    double *row = SM(double, F.o_row);           // gene scores, clade-major CSR
+    u16 *hp = SM(u16, F.o_row);                  // sort permutation of the staged hits (dead before `row` is written)
     int *cl_id = SM(int, F.o_clid);
-    u32 *mk0 = SM(u32, F.o_mk0), *mk1 = SM(u32, F.o_mk1), *mk2 = SM(u32, F.o_mk2);
-    u16 *cl_head = SM(u16, F.o_clhead), *cl_tail = SM(u16, F.o_cltail);
-    double *g_score = SM(double, F.o_gscore);   // running sum v * (newly covered sites) while the locus streams, then the score
-    u32 *g_u = SM(u32, F.o_gu);                 // [Kcap] union of the better hits of the CURRENT locus' groups: ua | ub << 16
-    u16 *g_t = SM(u16, F.o_gt), *g_next = SM(u16, F.o_gnext);
-    u8 *g_loc = SM(u8, F.o_gloc);               // locus of the group (bit 7: a hit left a gap -> generic sweep)
+    u32 *mk0 = SM(u32, F.o_mk0), *mk1 = SM(u32, F.o_mk1), *mk2 = SM(u32, F.o_mk2), *pres = SM(u32, F.o_pres);
+    u16 *cstart = SM(u16, F.o_cstart);
+    char *xs = SM(char, F.o_x);                  // search scratch (aliases rec / gstart / g_t / g_loc)
     unsigned long long *stat = SM(unsigned long long, F.o_stat);   // per-warp counters, flushed once at exit
-    int *t_count = reinterpret_cast<int *>(stat + 8);              // clades of the current level
-    char *scratch = a.scratch + ((size_t)blockIdx.x * FAST_WPC + wid) * (size_t)F.Kcap * 16;
+    char *gscr = a.scratch + ((size_t)blockIdx.x * FAST_WPC + wid) * (size_t)F.scratch_bytes;
+    char *cold = gscr;                           // record arrays of the cold gene-score paths
     enum { ST_PAIRS, ST_GROUPS, ST_LEVELS, ST_PTEST, ST_PSCORE, ST_DONE, ST_REFINED, ST_TRIPS, ST_N };
     if (lane < ST_N) stat[lane] = 0;
     __syncwarp();
@@ -396,7 +353,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
         c = __shfl_sync(FULL, c, 0);
         if (c < 0) break;
         const long long h0 = a.b.hit_off[c], l0 = a.b.locus_off[c];
-        const int H = (int)(a.b.hit_off[c + 1] - h0), Graw = (int)(a.b.locus_off[c + 1] - l0);
+        const int H = (int)min((long long)0x7fffffff, a.b.hit_off[c + 1] - h0), Graw = (int)(a.b.locus_off[c + 1] - l0);
         bool fallback = false, trip = false;
         int reason = 0;   // why the contig goes to the next pass: 0 loci, 1 hits, 2 coordinates, 3 records, 4 clades, 5 groups, 6 pairs, 7 guard
         FOut R{WFL_CALL_UNCLASSIFIED, 0, -1, -1, -1, -1, -1, 0, 0, H > 0 ? P.p.jump_taxonomy : 0, 0, 0.0, 0.0};
@@ -435,341 +392,358 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
         }
         if (G > GMAX) fallback = true;
         fallback = __any_sync(FULL, fallback);
+        if (lane < GMAX) l_cur[lane] = 0;
         __syncwarp();
         const u32 allG = G >= 32 ? 0xffffffffu : ((1u << G) - 1u);
         // a locus without an entry scores 0 (waafle_orgscorer.py:404-405): its mask bit is (0 >= threshold)
-        const u32 init0 = thr3[0] <= 0.0 ? allG : 0u, init1 = thr3[1] <= 0.0 ? allG : 0u, init2 = 0u;
+        const u32 init0 = thr3[0] <= 0.0 ? allG : 0u, init1 = thr3[1] <= 0.0 ? allG : 0u;
 
-        // ---- K1, once per contig (level-invariant): which hit is attached to which locus (attach_hits :359-369) ----
-        int M = 0;
+        // ---- K1, once per contig: one pass over the hit columns (attach_hits :359-369); attached hits are staged ----
+        int Hs = 0;   // staged entries == records of the contig
         if (!fallback && H > 0 && G > 0) {
-            if (H > F.Hcap) {
-                fallback = true;
-                reason = 1;
-            } else {
-                // (a) one pass over the hits: span, filter flags and the mask of the loci each hit is attached to
-                bool big = false;
-                const u8 fmask = P.p.stranded ? 3 : 1;
-#pragma unroll 2
-                for (int base = 0; base < H; base += 32) {
-                    const int h = base + lane;
-                    if (h < H) {
-                        int q1, q2;
-                        hits.span(h0 + h, q1, q2);
-                        const int hmin = min(q1, q2), hmax = max(q1, q2);
-                        big |= hmin < 0 || hmax > 65535;
-                        const u8 fl = hits.flags(h0 + h);
-                        u32 mb = 0;
-                        if (fl & 1) {   // scov_modified >= --min-scov (:362)
+            bool big = false, bad = false;
+            const int *anc0 = a.anc + (size_t)min(R.lifts, a.anc_rows - 1) * (size_t)tax.n_nodes;
 #pragma unroll 1
-                            for (int i = 0; i < G; ++i) {
-                                const int lmin = l_lo[i], llen = l_len[i], lmax = lmin + llen - 1;
-                                if (lmin > hmax || hmin > lmax) continue;
-                                if (P.p.stranded) {   // hit.sstrand == locus.strand (:365)
-                                    const signed char ls = l_str[i];
-                                    if (!((ls == '-' && (fl & 2)) || (ls == '+' && !(fl & 2)))) continue;
-                                }
-                                if (overlap_ok(hmin, hmax, lmin, lmax, llen, P.p.min_overlap)) mb |= 1u << i;
+            for (int base = 0; base < H; base += 32) {
+                const int h = base + lane;
+                u32 mb = 0;
+                int hmin = 0, hmax = 0;
+                if (h < H) {
+                    int q1, q2;
+                    hits.span(h0 + h, q1, q2);
+                    hmin = min(q1, q2);
+                    hmax = max(q1, q2);
+                    big |= hmin < 0 || hmax > 65535;
+                    const u8 fl = hits.flags(h0 + h);
+                    if (fl & 1) {   // scov_modified >= --min-scov (:362)
+#pragma unroll 1
+                        for (int i = 0; i < G; ++i) {
+                            const int lmin = l_lo[i], llen = l_len[i], lmax = lmin + llen - 1;
+                            if (lmin > hmax || hmin > lmax) continue;
+                            if (P.p.stranded) {   // hit.sstrand == locus.strand (:365)
+                                const signed char ls = l_str[i];
+                                if (!((ls == '-' && (fl & 2)) || (ls == '+' && !(fl & 2)))) continue;
+                            }
+                            if (overlap_ok(hmin, hmax, lmin, lmax, llen, P.p.min_overlap)) mb |= 1u << i;
+                        }
+                    }
+                }
+                // one staged ENTRY per (hit, locus) match, in hit order (a hit is rarely attached to more than one locus)
+                int tot;
+                const int ex = warp_excl_scan(__popc(mb), tot);
+                if (mb) {
+                    const int tx = hits.taxon(h0 + h);
+                    const double sc = a.b.hit_score[h0 + h];
+                    int cl = tax.root;
+                    if ((u32)tx >= (u32)tax.n_nodes) bad = true;   // malformed input: the exact pipeline reports it
+                    else cl = R.lifts ? anc0[tx] : tx;             // row 0 of the ancestor table is the identity
+                    int s = Hs + ex;
+                    u32 m2 = mb;
+#pragma unroll 1
+                    while (m2) {
+                        const int i = __ffs(m2) - 1;
+                        m2 &= m2 - 1u;
+                        if (s < F.Hcap) {
+                            hv[s] = sc > 0.0 ? sc : 0.0;
+                            hsp[s] = (u32)(hmin & 0xffff) | ((u32)(hmax & 0xffff) << 16);
+                            hcl[s] = cl;
+                            hloc[s] = (u8)i;
+                            if (S > 0) hid[s] = (u16)h;
+                        }
+                        ++s;
+                    }
+                }
+                Hs += tot;
+                // entries per locus
+                u32 m2 = mb;
+#pragma unroll 1
+                while (__any_sync(FULL, m2 != 0u)) {
+                    const int i = m2 ? __ffs(m2) - 1 : -1;
+                    const u32 peers = __match_any_sync(FULL, i >= 0 ? i : 64 + lane);
+                    if (i >= 0 && (peers & lt_mask()) == 0u) l_cur[i] += (u16)__popc(peers);
+                    m2 &= m2 - 1u;
+                    __syncwarp();
+                }
+            }
+            big = __any_sync(FULL, big);
+            bad = __any_sync(FULL, bad);
+            if (big) { fallback = true; reason = 2; }          // spans are staged in 16 bits
+            else if (bad) { fallback = true; reason = 4; }
+            else if (H > 65535) { fallback = true; reason = 1; }
+            else if (Hs > F.Hcap) { fallback = true; reason = 3; }
+            // locus-major record layout
+            int cnt = lane < G ? (int)l_cur[lane] : 0;
+            int tot;
+            const int ex = warp_excl_scan(cnt, tot);
+            if (lane <= G && lane < GMAX) l_base[lane] = (u16)min(ex, 0xffff);
+            if (lane == 0 && G == GMAX) l_base[GMAX] = (u16)min(tot, 0xffff);
+            __syncwarp();
+            // ---- K3: annotation winners, level-independent (score_hit :384-392): the LAST hit attaining the max score
+            //      per (locus, system), two phases of shared-memory atomics (score bits, then hit index) ----
+            if (S > 0 && !fallback) {
+                int *annw = reinterpret_cast<int *>(unk_row);
+#pragma unroll 1
+                for (int s2 = 0; s2 < S; ++s2) {
+                    if (lane < GMAX) { maxb[lane] = 0ull; annw[lane] = -1; }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll 1
+                        for (int j = lane; j < Hs; j += 32) {
+                            const int hh = hid[j], i = hloc[j];
+                            const double sc = a.b.hit_score[h0 + hh];
+                            if (((hits.sysmask(h0 + hh) >> s2) & 1u) && sc >= P.ann_thr) {
+                                const u64 sb = dbits(sc);
+                                if (phase == 0) atomicMax(&maxb[i], sb);
+                                else if (maxb[i] == sb) atomicMax(&annw[i], hh);
                             }
                         }
-                        hsp[h] = (u32)(hmin & 0xffff) | ((u32)(hmax & 0xffff) << 16);
-                        hmk[h] = mb;
+                        __syncwarp();
                     }
-                }
-                (void)fmask;
-                if (__any_sync(FULL, big)) { fallback = true; reason = 2; }   // spans are staged in 16 bits
-                __syncwarp();
-            }
-            // (b) one compaction pass per locus over the staged masks: records come out locus-major, hit order inside
-#pragma unroll 1
-            for (int i = 0; i < G && !fallback; ++i) {
-                const int lmin = l_lo[i], llen = l_len[i];
-                if (lane == 0) l_base[i] = (u16)M;
-                const int m0 = M;
-#pragma unroll 2
-                for (int base = 0; base < H; base += 32) {
-                    const int h = base + lane;
-                    const bool mt = h < H && ((hmk[h] >> i) & 1u);
-                    const u32 m = __ballot_sync(FULL, mt);
-                    if (mt) {
-                        const int slot = M + __popc(m & lt_mask());
-                        if (slot < F.Mcap) {
-                            const u32 sp = hsp[h];
-                            const int hmin = (int)(sp & 0xffffu), hmax = (int)(sp >> 16);
-                            rec_hit[slot] = (u16)h;
-                            // python slice [h1 : h2+1] of the site array (:373-382)
-                            rec_ab[slot] = (u32)max(0, hmin - lmin) | ((u32)(min(llen - 1, hmax - lmin) + 1) << 16);
-                        }
-                    }
-                    M += __popc(m);
-                }
-                if (M > F.Mcap || M - m0 > F.Kcap) { fallback = true; reason = 3; }
-            }
-            if (lane == 0) l_base[G] = (u16)M;
-            __syncwarp();
-            // (c) every locus' records in DESCENDING SCORE order (ties: hit order), once per contig: the level loop streams
-            // them in that order, so that a clade's envelope only ever grows by "newly covered sites x score".  Loci that
-            // arrive sorted (the front end's packer sorts the hits of a contig by score) skip the rank-by-counting sort.
-            if (!fallback) {
-                double *tv = reinterpret_cast<double *>(hsp);                      // [Kcap] scores of the locus
-                u16 *th = reinterpret_cast<u16 *>(tv + F.Kcap);                    // [Kcap] sorted hit indices
-                u32 *tab = reinterpret_cast<u32 *>(th + F.Kcap + (F.Kcap & 1));    // [Kcap] sorted slices
-#pragma unroll 1
-                for (int i = 0; i < G; ++i) {
-                    const int r0 = l_base[i], k = (int)l_base[i + 1] - r0;
-                    if (k < 2) continue;
-#pragma unroll 2
-                    for (int j = lane; j < k; j += 32) tv[j] = a.b.hit_score[h0 + rec_hit[r0 + j]];
-                    __syncwarp();
-                    bool sorted = true;
-#pragma unroll 1
-                    for (int j = lane; j + 1 < k; j += 32) sorted &= tv[j] >= tv[j + 1];
-                    if (__all_sync(FULL, sorted)) continue;
-#pragma unroll 1
-                    for (int j = lane; j < k; j += 32) {
-                        const double v = tv[j];
-                        int rk = 0;
-#pragma unroll 4
-                        for (int q = 0; q < k; ++q) {
-                            const double vq = tv[q];
-                            rk += (vq > v) || (vq == v && q < j);
-                        }
-                        th[rk] = rec_hit[r0 + j];
-                        tab[rk] = rec_ab[r0 + j];
-                    }
-                    __syncwarp();
-#pragma unroll 1
-                    for (int j = lane; j < k; j += 32) {
-                        rec_hit[r0 + j] = th[j];
-                        rec_ab[r0 + j] = tab[j];
-                    }
+                    if (lane < G) a.o.ann_winner[(l0 + l_raw[lane]) * S + s2] = annw[lane] >= 0 ? (int)(h0 + annw[lane]) : -1;
                     __syncwarp();
                 }
             }
+        } else if (lane <= GMAX && lane <= G) {
+            l_base[lane] = 0;
         }
+        __syncwarp();
 
         int iter = 0;
 #pragma unroll 1
         while (!fallback && !finished && H > 0 && G > 0) {
             // ============================ one taxonomy level ============================
-            const int *anc = a.anc + (size_t)min(R.lifts, a.anc_rows - 1) * (size_t)tax.n_nodes;
-            int N = 0, ovf_reason = 4;
-            bool ovf = false;
-            if (lane == 0) *t_count = 0;
-#pragma unroll 1
-            for (int s = lane; s <= F.cmask; s += 32) hkey[s] = EMPTY_KEY;
-            __syncwarp();
-            if (spike)   // "Unknown" is a clade of every level (waafle_orgscorer.py:416-418): handle 0
-                (void)clade_handle(hkey, hval, cl_id, mk0, mk1, mk2, cl_head, cl_tail, t_count, F.cmask, F.Tcap, 0u, 0u, 0u,
-                                   tax.unknown, lane == 0, ovf);
-            const int t_unk = spike ? 0 : -1;
             if (lane == 0) ++stat[ST_LEVELS];
-
+            // ---- order of the level: staged hits by (clade, score descending); checked, sorted only if needed ----
+            bool ident = true;
+            {
+                bool ok = true;
 #pragma unroll 1
-            for (int i = 0; i < G; ++i) {
-                const int llen = l_len[i];
-                const int r0 = l_base[i], k = (int)l_base[i + 1] - r0;
-                const int N0 = N;
-                if (iter == 0 && lane == 0) stat[ST_PAIRS] += (unsigned long long)k;
-                if (k == 0) { if (lane == 0) maxv[i] = 0.0; continue; }
-
-                // ---- K3: annotation winners, level-independent (score_hit :384-392): last hit with the max score ----
-                if (S > 0 && iter == 0) {
+                for (int j = lane + 1; j < Hs; j += 32) {
+                    const int c0 = hcl[j - 1], c1 = hcl[j];
+                    ok &= c0 < c1 || (c0 == c1 && hv[j - 1] >= hv[j]);
+                }
+                ident = __all_sync(FULL, ok);
+            }
+            if (!ident) {
+                int Pn = 32;
+                while (Pn < Hs) Pn <<= 1;
 #pragma unroll 1
-                    for (int s2 = 0; s2 < S; ++s2) {
-                        u64 bb = 0;
-                        long long bw = -1;
+                for (int j = lane; j < Pn; j += 32) hp[j] = (u16)(j < Hs ? j : NONE16);
+                __syncwarp();
 #pragma unroll 1
-                        for (int r = lane; r < k; r += 32) {
-                            const int hh = rec_hit[r0 + r];
-                            const double sc = a.b.hit_score[h0 + hh];
-                            if (((hits.sysmask(h0 + hh) >> s2) & 1u) && sc >= P.ann_thr) {
-                                const u64 sb = dbits(sc);
-                                if (sb > bb || (sb == bb && hh > bw)) { bb = sb; bw = hh; }
-                            }
+                for (int k = 2; k <= Pn; k <<= 1) {
+#pragma unroll 1
+                    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+#pragma unroll 1
+                        for (int x = lane; x < (Pn >> 1); x += 32) {
+                            const int lo = ((x & ~(jj - 1)) << 1) | (x & (jj - 1)), hi = lo | jj;
+                            const int u = hp[lo], w = hp[hi];
+                            const bool up = (lo & k) == 0;
+                            if (hit_after(hcl, hv, u, w) == up) { hp[lo] = (u16)w; hp[hi] = (u16)u; }
                         }
-                        const u64 mx = warp_max_u64(bb);
-                        const long long w = warp_max_ll((mx != 0 && bb == mx) ? bw : -1);
-                        if (lane == 0) a.o.ann_winner[(l0 + l_raw[i]) * S + s2] = w >= 0 ? (int)(h0 + w) : -1;
+                        __syncwarp();
                     }
                 }
+            }
 
-                // ---- K2: stream the locus' records in score order; every clade's envelope state grows in place ----
-                // (the next tile's hit data is requested before the current tile is processed)
-                u32 ab_n = 0;
-                int tx_n = 0;
-                double sc_n = 0.0;
-                if (lane < k) {
-                    const long long h = h0 + rec_hit[r0 + lane];
-                    ab_n = rec_ab[r0 + lane];
-                    tx_n = hits.taxon(h);
-                    sc_n = a.b.hit_score[h];
+            // ---- clades of the level (runs of equal clade: handles in ascending node index) and, in the same pass,
+            //      the records (locus-major) and the (clade, locus) groups ----
+            int T = 0, N = 0, t_unk = -1;
+            bool ovf = false;
+            int ovf_reason = 4;
+            {
+                if (lane < G) {
+                    l_cur[lane] = l_base[lane];
+                    l_last[lane] = (u16)NONE16;
+                    maxb[lane] = dbits(0.0);
                 }
+                __syncwarp();
+                int run = 0, n_lt = 0, carry = -1;
+                bool seen_unk = false;
+                const int unk_id = tax.unknown;
 #pragma unroll 1
-                for (int base = 0; base < k; base += 32) {
+                for (int base = 0; base < Hs; base += 32) {
                     const int j = base + lane;
-                    bool act = j < k;
-                    const u32 ab = ab_n;
-                    const int tx = tx_n;
-                    const double sc = sc_n;
-                    if (j + 32 < k) {
-                        const long long h = h0 + rec_hit[r0 + j + 32];
-                        ab_n = rec_ab[r0 + j + 32];
-                        tx_n = hits.taxon(h);
-                        sc_n = a.b.hit_score[h];
+                    const bool act = j < Hs;
+                    const int h = act ? (ident ? j : (int)hp[j]) : 0;
+                    const int cl = act ? hcl[h] : 0x7fffffff;
+                    int up = __shfl_up_sync(FULL, cl, 1);
+                    if (lane == 0) up = carry;
+                    const bool head = act && cl != up;
+                    const u32 hb = __ballot_sync(FULL, head);
+                    int t = run + __popc(hb & le_mask) - 1;
+                    bool isunk = false;
+                    if (spike) {
+                        // "Unknown" is a clade of every level (waafle_orgscorer.py:416-418): its handle is inserted in
+                        // node-index order if no hit carries it
+                        const u32 ltb = __ballot_sync(FULL, act && cl < unk_id), eqb = __ballot_sync(FULL, act && cl == unk_id);
+                        seen_unk |= eqb != 0u;
+                        n_lt += __popc(hb & ltb);
+                        if (!seen_unk && act && cl > unk_id) ++t;
+                        isunk = act && cl == unk_id;
                     }
-                    double v = 0.0;
-                    int cl = tax.root;
-                    if (act) {
-                        if ((u32)tx >= (u32)tax.n_nodes) ovf = true;   // malformed input: the exact pipeline reports it
-                        else cl = R.lifts ? anc[tx] : tx;              // row 0 of the ancestor table is the identity
-                        v = sc > 0.0 ? sc : 0.0;                       // sites start at 0 (np.zeros, :381)
-                    }
-                    const int t = clade_handle(hkey, hval, cl_id, mk0, mk1, mk2, cl_head, cl_tail, t_count, F.cmask, F.Tcap,
-                                               init0, init1, init2, cl, act, ovf);
-                    // with "assign-unknown" the hits of a taxon NAMED Unknown carry no gene score: the spiked row replaces
-                    // gene_scores["Unknown"] (waafle_orgscorer.py:416-418)
-                    if (t == t_unk) act = false;
-                    const u32 peers = __match_any_sync(FULL, act ? t : 0x10000 + lane);
-                    const int leader = __ffs(peers) - 1;
-                    int g = -1;
-                    bool cont = false;
-                    if (act && lane == leader) {   // the clade's group of THIS locus, if an earlier tile opened it
-                        const int tail = cl_tail[t];
-                        if (tail != NONE16 && (int)(g_loc[tail] & 0x3f) == i) { g = tail; cont = true; }
-                    }
-                    const bool newg = act && lane == leader && !cont;
-                    const u32 nm = __ballot_sync(FULL, newg);
-                    if (newg) {
-                        g = N + __popc(nm & lt_mask());
-                        if (g < F.Ncap) {
-                            g_t[g] = (u16)t;
-                            g_loc[g] = (u8)i;
-                            g_next[g] = (u16)NONE16;
-                            const int tail = cl_tail[t];   // rows: groups of a clade linked in locus order
-                            if (tail != NONE16) g_next[tail] = (u16)g; else cl_head[t] = (u16)g;
-                            cl_tail[t] = (u16)g;
+                    if (head) {
+                        if (t < F.Tcap) {
+                            cl_id[t] = cl;
+                            mk0[t] = init0; mk1[t] = init1; mk2[t] = 0u;
+                            pres[t] = 0u;
+                        } else {
+                            ovf = true;
                         }
                     }
-                    N += __popc(nm);
-                    if (act && N <= F.Ncap) {
-                        g = __shfl_sync(peers, g, leader);
-                        cont = __shfl_sync(peers, (int)cont, leader) != 0;
-                        int ua, ub;
-                        double sum;
-                        bool cplx = false;
-                        u32 rest = peers;
-                        if (cont) {
-                            const u32 u = g_u[g - N0];
-                            ua = (int)(u & 0xffffu);
-                            ub = (int)(u >> 16);
-                            sum = g_score[g];
-                        } else {   // the group opens with its best hit
-                            const u32 ab0 = __shfl_sync(peers, ab, leader);
-                            const double v0 = __shfl_sync(peers, v, leader);
-                            ua = (int)(ab0 & 0xffffu);
-                            ub = (int)(ab0 >> 16);
-                            sum = v0 * (double)(ub - ua);
-                            rest &= rest - 1;
+                    run += __popc(hb);
+                    carry = __shfl_sync(FULL, cl, 31);
+                    if (__any_sync(FULL, ovf) || run + 1 > F.Tcap) { ovf = true; break; }
+                    __syncwarp();
+                    // records (locus-major, this order inside a locus) and groups of this tile
+                    {
+                        const int i = act ? (int)hloc[h] : -1;
+                        const u32 peers = __match_any_sync(FULL, act ? i : 64 + lane);
+                        const u32 below = peers & lt_mask();
+                        const int pt_lane = __shfl_sync(FULL, t, below ? 31 - __clz(below) : lane);
+                        bool gh = false;
+                        int slot = 0;
+                        if (act) {
+                            slot = (int)l_cur[i] + __popc(below);
+                            rec[slot] = (u16)h;
+                            const int pt = below ? pt_lane : (int)l_last[i];
+                            // with "assign-unknown" the hits of a taxon NAMED Unknown carry no gene score: the spiked row
+                            // replaces gene_scores["Unknown"] (:416-418)
+                            gh = pt != t && !isunk;
                         }
-#pragma unroll 1
-                        while (rest) {   // the clade's other hits of this tile, in score order
-                            if (ua == 0 && ub == llen) break;   // the union covers the gene: nothing can be added
-                            const int p = __ffs(rest) - 1;
-                            rest &= rest - 1;
-                            const u32 abp = __shfl_sync(peers, ab, p);
-                            const double vp = __shfl_sync(peers, v, p);
-                            if (vp > 0.0) {
-                                const int pa = (int)(abp & 0xffffu), pb = (int)(abp >> 16);
-                                if (pa > ub || pb < ua) {
-                                    cplx = true;   // a gap: the union is no longer one interval
-                                } else {
-                                    const int add = max(0, ua - pa) + max(0, pb - ub);
-                                    if (add) sum += vp * (double)add;
-                                    ua = min(ua, pa);
-                                    ub = max(ub, pb);
-                                }
+                        const u32 gb = __ballot_sync(FULL, gh);
+                        if (gh) {
+                            const int g = N + __popc(gb & lt_mask());
+                            if (g < F.Ncap) {
+                                gstart[g] = (u16)slot;
+                                g_t[g] = (u16)t;
+                                g_loc[g] = (u8)i;
                             }
+                            atomicOr(&pres[t], 1u << i);
                         }
-                        if (lane == leader) {
-                            g_u[g - N0] = (u32)ua | ((u32)ub << 16);
-                            g_score[g] = sum;
-                            if (cplx) g_loc[g] |= 0x80;
-                        }
-                    }
-                    // the next tile reads this tile's state: clade_handle() synchronises the warp first
-                }
-                if (N > F.Ncap) { ovf = true; ovf_reason = 5; }
-                ovf = __any_sync(FULL, ovf);
-                if (ovf) break;
-                __syncwarp();
-
-                // ---- the locus' groups are complete: gene scores, guard band, masks, per-locus max ----
-                u64 mxb = dbits(0.0);
-                const double dn = (double)llen;
-#pragma unroll 1
-                for (int base = N0; base < N; base += 32) {
-                    const int g = base + lane;
-                    const bool act = g < N;
-                    int t = 0;
-                    bool cplx = false;
-                    double sc = 0.0;
-                    if (act) {
-                        t = g_t[g];
-                        cplx = (g_loc[g] & 0x80) != 0;
-                        sc = g_score[g] / dn;
-                    }
-                    // groups whose hits left a gap: generic endpoint sweep; scores inside the guard band of a threshold:
-                    // recomputed in numpy's summation order.  Both cold, one lane at a time (global scratch of the warp).
-                    u32 cm = __ballot_sync(FULL, act && cplx);
-#pragma unroll 1
-                    while (cm) {
-                        const int ln = __ffs(cm) - 1;
-                        cm &= cm - 1;
-                        if (lane == ln) sc = group_slow(a, hits, scratch, F.Kcap, rec_hit, rec_ab, h0, r0, k, anc, cl_id[t], llen, false);
+                        N += __popc(gb);
                         __syncwarp();
-                    }
-                    const bool near = act && (fabs(sc - thr3[0]) <= GUARD || fabs(sc - thr3[1]) <= GUARD ||
-                                              fabs(sc - thr3[2]) <= GUARD);
-                    u32 nm = __ballot_sync(FULL, near);
-#pragma unroll 1
-                    while (nm) {
-                        const int ln = __ffs(nm) - 1;
-                        nm &= nm - 1;
-                        if (lane == ln) {
-                            sc = group_slow(a, hits, scratch, F.Kcap, rec_hit, rec_ab, h0, r0, k, anc, cl_id[t], llen, true);
-                            atomicAdd(&stat[ST_REFINED], 1ull);
+                        if (act && (peers >> lane) == 1u) {   // last of its locus in this tile
+                            l_cur[i] = (u16)(slot + 1);
+                            l_last[i] = (u16)t;
                         }
                         __syncwarp();
                     }
-                    if (act) {
-                        g_score[g] = sc;
-                        g_loc[g] = (u8)i;
-                        const u32 bit = 1u << i;
-                        mk0[t] = sc >= thr3[0] ? (mk0[t] | bit) : (mk0[t] & ~bit);
-                        mk1[t] = sc >= thr3[1] ? (mk1[t] | bit) : (mk1[t] & ~bit);
-                        mk2[t] = sc >= thr3[2] ? (mk2[t] | bit) : (mk2[t] & ~bit);
-                        if (cl_id[t] != tax.unknown) {   // waafle_orgscorer.py:409-411
-                            const u64 sb = dbits(sc);
-                            mxb = sb > mxb ? sb : mxb;
+                    if (N > F.Ncap) { ovf = true; ovf_reason = 5; break; }
+                }
+                T = run;
+                if (spike && !ovf) {
+                    t_unk = n_lt;
+                    if (!seen_unk) {
+                        if (lane == 0) {
+                            cl_id[t_unk] = unk_id;
+                            mk0[t_unk] = mk1[t_unk] = mk2[t_unk] = 0u;
+                            pres[t_unk] = 0u;
                         }
+                        ++T;
                     }
                 }
-                mxb = warp_max_u64(mxb);
-                if (lane == 0) maxv[i] = dbits_inv(mxb);
-                __syncwarp();
             }
             ovf = __any_sync(FULL, ovf);
             if (ovf) { fallback = true; reason = ovf_reason; break; }
-            if (lane == 0) stat[ST_GROUPS] += (unsigned long long)N;
             __syncwarp();
-            const int T = *t_count;
+            if (lane == 0) {
+                stat[ST_GROUPS] += (unsigned long long)N;
+                if (iter == 0) stat[ST_PAIRS] += (unsigned long long)Hs;
+            }
+
+            // ---- rows: clade-major CSR through the presence masks ----
+            {
+                int acc = 0;
+#pragma unroll 1
+                for (int base = 0; base < T; base += 32) {
+                    const int t = base + lane;
+                    const int cnt = t < T ? __popc(pres[t]) : 0;
+                    int tot;
+                    const int ex = warp_excl_scan(cnt, tot);
+                    if (t < T) cstart[t] = (u16)(acc + ex);
+                    acc += tot;
+                }
+            }
+            __syncwarp();
+
+            // ---- K2: gene scores, one lane per (clade, locus) group; guard band, masks, per-locus max ----
+#pragma unroll 1
+            for (int base = 0; base < N; base += 32) {
+                const int g = base + lane;
+                const bool act = g < N;
+                int t = 0, i = 0, r0 = 0, cl = 0, llen = 1, lmin = 0, lend = 0;
+                bool cplx = false;
+                double sc = 0.0;
+                if (act) {
+                    t = g_t[g];
+                    i = g_loc[g];
+                    r0 = gstart[g];
+                    cl = cl_id[t];
+                    llen = l_len[i];
+                    lmin = l_lo[i];
+                    lend = l_base[i + 1];
+                    int h = rec[r0];
+                    int ua, ub;
+                    hit_slice(hsp[h], lmin, llen, ua, ub);
+                    double sum = hv[h] * (double)(ub - ua);   // the group opens with its best hit
+#pragma unroll 1
+                    for (int q = r0 + 1; q < lend; ++q) {
+                        if (ua == 0 && ub == llen) break;      // the union covers the gene: nothing can be added
+                        h = rec[q];
+                        if (hcl[h] != cl) break;
+                        const double vp = hv[h];
+                        if (!(vp > 0.0)) break;                // descending: the rest contributes nothing
+                        int pa, pb;
+                        hit_slice(hsp[h], lmin, llen, pa, pb);
+                        if (pa > ub || pb < ua) { cplx = true; break; }   // a gap: the union is no longer one interval
+                        const int add = max(0, ua - pa) + max(0, pb - ub);
+                        if (add) sum += vp * (double)add;
+                        ua = min(ua, pa);
+                        ub = max(ub, pb);
+                    }
+                    sc = sum / (double)llen;
+                }
+                // groups whose hits left a gap: generic endpoint sweep; scores inside the guard band of a threshold:
+                // recomputed in numpy's summation order.  Both cold, one lane at a time (global scratch of the warp).
+                u32 cm = __ballot_sync(FULL, act && cplx);
+#pragma unroll 1
+                while (cm) {
+                    const int ln = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    if (lane == ln) sc = group_slow(a, cold, F.Hcap, rec, hsp, hcl, hv, r0, lend, cl, lmin, llen, false);
+                    __syncwarp();
+                }
+                const bool near = act && (fabs(sc - thr3[0]) <= GUARD || fabs(sc - thr3[1]) <= GUARD ||
+                                          fabs(sc - thr3[2]) <= GUARD);
+                u32 nm = __ballot_sync(FULL, near);
+#pragma unroll 1
+                while (nm) {
+                    const int ln = __ffs(nm) - 1;
+                    nm &= nm - 1;
+                    if (lane == ln) {
+                        sc = group_slow(a, cold, F.Hcap, rec, hsp, hcl, hv, r0, lend, cl, lmin, llen, true);
+                        atomicAdd(&stat[ST_REFINED], 1ull);
+                    }
+                    __syncwarp();
+                }
+                if (act) {
+                    const u32 pm = pres[t], bit = 1u << i;
+                    row[(int)cstart[t] + __popc(pm & (bit - 1u))] = sc;
+                    if (sc >= thr3[0]) atomicOr(&mk0[t], bit); else if (init0) atomicAnd(&mk0[t], ~bit);
+                    if (sc >= thr3[1]) atomicOr(&mk1[t], bit); else if (init1) atomicAnd(&mk1[t], ~bit);
+                    if (sc >= thr3[2]) atomicOr(&mk2[t], bit);
+                    if (cl != tax.unknown) atomicMax(&maxb[i], dbits(sc));   // waafle_orgscorer.py:409-411
+                }
+            }
+            __syncwarp();
 
             // ---- K4: weak loci (update_gene_scores :407-429) ----
             bool ign = false;
             double mx = 0.0;
             if (lane < G) {
-                mx = maxv[lane];
+                mx = dbits_inv(maxb[lane]);
                 ign = P.p.weak_loci == 0 ? !(mx >= P.min_thr) : false;
             }
             const u32 um = __ballot_sync(FULL, lane < G && !ign);
@@ -788,7 +762,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 const u32 m0 = __ballot_sync(FULL, lane < G && u >= thr3[0]);
                 const u32 m1 = __ballot_sync(FULL, lane < G && u >= thr3[1]);
                 const u32 m2 = __ballot_sync(FULL, lane < G && u >= thr3[2]);
-                if (lane == 0) { mk0[0] = m0; mk1[0] = m1; mk2[0] = m2; }
+                if (lane == 0) { mk0[t_unk] = m0; mk1[t_unk] = m1; mk2[t_unk] = m2; }
             }
             __syncwarp();
             if (iter == 0 && nun == 0) { finished = true; break; }   // "empty" contig (:959): unclassified
@@ -798,13 +772,11 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
             for (int t = lane; t < T; t += 32) hasroot |= cl_id[t] == tax.root;
             hasroot = __any_sync(FULL, hasroot);
 
-            FLevel L{G, T, t_unk, um, nun, cl_head, g_next, g_loc, g_score, unk_row, cl_id, {mk0, mk1, mk2}, l_len, hkey};
+            int *cl_par = reinterpret_cast<int *>(xs + ((2 * F.Tcap + 15) & ~15));   // after the two-clade candidates
+            FLevel L{G, T, t_unk, um, nun, pres, cstart, row, unk_row, cl_id, {mk0, mk1, mk2}, l_len, cl_par};
 
             // ---- K6: one-clade search (explain_one :585-597) ----
             {
-                // ranks of the passing clades are kept for the meld pass (in the scratch area, if they fit)
-                double *rcache = reinterpret_cast<double *>(xs);
-                const bool cached = T * 8 <= F.x_bytes;
                 u64 bbits = 0;
                 int bid = -1, btl = -1;
                 double bcrit = 0.0;
@@ -813,7 +785,6 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     if ((mk0[t] & um) != um) continue;   // crit >= k1
                     double crit;
                     const double rank = row_stats(L, t, -1, &crit);
-                    if (cached) rcache[t] = rank;
                     const u64 b = dbits(rank);
                     if (b > bbits || (b == bbits && cl_id[t] > bid)) { bbits = b; bid = cl_id[t]; btl = t; bcrit = crit; }
                 }
@@ -828,7 +799,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     // meld_one (:621-631): options within --range of the best; guard the arg-max and the range edge
                     int my = -1, nk = 0;
                     bool near = false;
-                    int *klist = hkey;   // kept clades (node ids); the hash is dead after the loci loop
+                    int *klist = reinterpret_cast<int *>(xs);   // kept clades (node ids), ascending
                     int kbase = 0;
 #pragma unroll 1
                     for (int base = 0; base < T; base += 32) {
@@ -836,7 +807,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         bool kept = false;
                         if (t < T && (mk0[t] & um) == um) {
                             double crit;
-                            const double rank = t == tb ? brank : (cached ? rcache[t] : row_stats(L, t, -1, &crit));
+                            const double rank = t == tb ? brank : row_stats(L, t, -1, &crit);
                             const double d = brank - rank;
                             if (t != tb && fabs(d) <= GUARD) near = true;
                             if (P.p.disambiguate_one == 1 && fabs(d - P.p.range) <= GUARD) near = true;
@@ -866,7 +837,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         long long mb = 0;
                         if (lane == 0) mb = (long long)atomicAdd(&a.ctr->mem_pool_used, (unsigned long long)R.na);
                         R.mem = __shfl_sync(FULL, mb, 0);
-                        emit_members_sorted(a, klist, R.na, R.mem, lane);
+#pragma unroll 1
+                        for (int j = lane; j < R.na; j += 32)
+                            if (R.mem + j < a.o.mem_pool_cap) a.o.mem_pool[R.mem + j] = klist[j];
                     }
                     finished = true;
                     break;
@@ -888,8 +861,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 __syncwarp();
                 const int NP = T2 * (T2 - 1) / 2;
                 if (lane == 0) stat[ST_PTEST] += (unsigned long long)NP;
-                // survivors of the mask prefilter follow the candidates in the scratch area
-                u16 *s_a = reinterpret_cast<u16 *>(xs + ((2 * F.Tcap + 15) & ~15)), *s_b = s_a + F.Scap;
+                // scratch after the candidates and the clade parents: melded-member flags, survivors of the mask prefilter
+                u8 *memA = reinterpret_cast<u8 *>(cl_par + F.Tcap), *memB = memA + F.Tcap;
+                u16 *s_a = reinterpret_cast<u16 *>(memB + ((F.Tcap + 15) & ~15)), *s_b = s_a + F.Scap;
                 double *s_rank = reinterpret_cast<double *>(s_b + F.Scap);
                 int nsurv = 0;
                 {
@@ -950,7 +924,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
 #pragma unroll 2
                         for (int t = lane; t < T; t += 32) {
                             const int id = cl_id[t];
-                            hkey[t] = tax.listed[id] ? tax.parent[id] : -1;
+                            cl_par[t] = tax.listed[id] ? tax.parent[id] : -1;
                         }
                         __syncwarp();
                     }
@@ -962,7 +936,6 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     double bcrit;
                     const double brank = row_stats(L, bi, bj, &bcrit);
                     // meld_two (:633-669) over the options within --range
-                    u8 *memA = reinterpret_cast<u8 *>(hval), *memB = memA + F.Tcap;   // the hash is dead
 #pragma unroll 1
                     for (int t = lane; t < T; t += 32) memA[t] = memB[t] = 0;
                     __syncwarp();
@@ -1022,8 +995,8 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                             a.o.synteny[l0 + l_raw[lane]] = ign ? '~' : (be.amb & m) ? '*' : (be.A & m) ? 'A' : (be.B & m) ? 'B' : '!';
                         }
                         if (melded) {
-                            // distinct melded clades per side, ascending node index (lists in the dead group scores)
-                            int *klist = reinterpret_cast<int *>(g_score);
+                            // distinct melded clades per side, ascending node index == handle order (lists in the dead rows)
+                            int *klist = reinterpret_cast<int *>(row);
 #pragma unroll 1
                             for (int side = 0; side < 2; ++side) {
                                 const u8 *mem = side ? memB : memA;
@@ -1042,8 +1015,11 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                             long long mb = 0;
                             if (lane == 0) mb = (long long)atomicAdd(&a.ctr->mem_pool_used, (unsigned long long)(R.na + R.nb));
                             R.mem = __shfl_sync(FULL, mb, 0);
-                            emit_members_sorted(a, klist, R.na, R.mem, lane);
-                            emit_members_sorted(a, klist + F.Tcap, R.nb, R.mem + R.na, lane);
+#pragma unroll 1
+                            for (int j = lane; j < R.na + R.nb; j += 32) {
+                                const int id = j < R.na ? klist[j] : klist[F.Tcap + j - R.na];
+                                if (R.mem + j < a.o.mem_pool_cap) a.o.mem_pool[R.mem + j] = id;
+                            }
                         }
                         finished = true;
                         break;
@@ -1051,11 +1027,13 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 }
             }
 
-            // ---- K9: not explained at this level: stop or lift (evaluate_contig :571-581) ----
+            // ---- K9: not explained at this level: stop or lift (evaluate_contig :571-581, raise_taxonomy :431-445) ----
             if (T == 0 || hasroot) { finished = true; break; }
             if (iter >= 100) { fallback = true; break; }   // runaway: the exact pipeline reports it
             ++R.lifts;
             ++iter;
+#pragma unroll 2
+            for (int j = lane; j < Hs; j += 32) hcl[j] = tax.parent[hcl[j]];
             __syncwarp();
         }
         if (H == 0 || G == 0) finished = !fallback;
@@ -1065,7 +1043,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
         if (fallback || trip || !finished) {
             if (lane == 0) {
                 // capacity overflows are worth a second pass with a larger slice; the rest goes straight to the exact pipeline
-                const bool retry = reason == 1 || reason == 3 || reason == 4 || reason == 5 || reason == 6;
+                const bool retry = (reason == 1 && H <= 65535) || reason == 3 || reason == 4 || reason == 5 || reason == 6;
                 const unsigned long long s = atomicAdd(retry ? a.fb_count : a.fb_final_count, 1ull);
                 (retry ? a.fb_list : a.fb_final)[s] = (int)c;
                 atomicAdd(&a.ctr->fb_reason[reason & 7], 1ull);
@@ -1097,44 +1075,53 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
 // host side
 // ---------------------------------------------------------------------------------------------
 // Slice layout for given capacities; returns the slice size in bytes (multiple of 16).
-//   Kcap records of one locus, Mcap records of the contig, Ccap clade-hash slots (power of two), Tcap clades and
-//   Ncap (clade, locus) groups per level.  Hcap (hits per contig) follows: the spans are staged over the per-level arrays.
-int fast_layout(FastCfg &F, int Kcap, int Mcap, int Ccap, int Tcap, int Ncap, int Scap) {
+//   Hcap attached hits and Mcap records of the contig, Tcap clades and Ncap (clade, locus) groups per level, Scap
+//   two-clade pairs that survive the mask prefilter.
+int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, int n_systems) {
     auto al = [](int x) { return (x + 15) & ~15; };
     int o = 0;
-    Ncap = std::max(Ncap, Tcap);                           // the two-clade member lists (2 x Tcap ints) reuse g_score
-    F.Kcap = Kcap; F.Mcap = Mcap; F.cmask = Ccap - 1; F.Tcap = Tcap; F.Ncap = Ncap;
-    F.o_stat = o; o += al(8 * 8 + 8);                      // 8 counters + the level's clade count
+    Hcap = std::min(std::max(Hcap, Mcap), 65534);         // staged entries ARE the records
+    Mcap = Hcap;
+    Tcap = std::min((Tcap + 15) & ~15, 65520);            // multiple of 16: the search scratch is carved in Tcap units
+    Ncap = std::min(std::max(Ncap, Tcap), 65534);          // the two-clade member lists (2 x Tcap ints) reuse the rows
+    int Pcap = 32;
+    while (Pcap < Hcap) Pcap <<= 1;
+    F.Hcap = Hcap; F.Pcap = Pcap; F.Mcap = Mcap; F.Tcap = Tcap; F.Ncap = Ncap;
+    F.Scap = (Scap + 1) & ~1;
+    F.o_stat = o; o += al(8 * 8 + 8);
     F.o_llo = o; o += al(4 * GMAX);
     F.o_llen = o; o += al(4 * GMAX);
     F.o_lraw = o; o += al(4 * GMAX);
     F.o_lstr = o; o += al(GMAX);
     F.o_lbase = o; o += al(2 * (GMAX + 2));
-    F.o_maxv = o; o += al(8 * GMAX);
+    F.o_lcur = o; o += al(2 * GMAX);
+    F.o_llast = o; o += al(2 * GMAX);
+    F.o_maxb = o; o += al(8 * GMAX);
     F.o_unk = o; o += al(8 * GMAX);
-    F.o_rhit = o; o += al(2 * Mcap);
-    F.o_rab = o; o += al(4 * Mcap);
-    // scratch: one-clade rank cache (Tcap doubles) | two-clade candidates (Tcap u16) + survivors (12 bytes each)
-    F.Scap = (Scap + 1) & ~1;
-    F.x_bytes = std::max(8 * Tcap, al(2 * Tcap) + 12 * F.Scap);
-    F.o_x = o; o += al(F.x_bytes);
-    const int lvl0 = o;
-    F.o_hkey = o; o += al(4 * Ccap);                       // also: one-clade member list, parents of the clades (Tcap ints)
-    F.o_hval = o; o += al(2 * Ccap);                       // also memA / memB (2 x Tcap bytes)
+    F.o_hv = o; o += al(8 * Hcap);
+    F.o_hsp = o; o += al(4 * Hcap);
+    F.o_hcl = o; o += al(4 * Hcap);
+    F.o_hid = o; o += n_systems > 0 ? al(2 * Hcap) : 0;
+    F.o_hloc = o; o += al(Hcap);
+    // per-level records and groups; the search scratch aliases them (dead once the gene scores are written):
+    //   two-clade: candidates (Tcap u16) | clade parents (Tcap int) | member flags (2 x Tcap u8) | survivors (12 B each)
+    //   one-clade: kept clades (Tcap int)
+    const int per_level = al(2 * Mcap) + al(2 * Ncap) + al(2 * Ncap) + al(Ncap);
+    F.x_bytes = std::max(per_level, al(2 * Tcap) + 4 * Tcap + 2 * al(Tcap) + 12 * F.Scap + 16);
+    F.o_rec = F.o_x = o;
+    F.o_gstart = F.o_rec + al(2 * Mcap);
+    F.o_gt = F.o_gstart + al(2 * Ncap);
+    F.o_gloc = F.o_gt + al(2 * Ncap);
+    o += al(F.x_bytes);
+    F.o_row = o; o += al(std::max(8 * Ncap, 2 * Pcap));
     F.o_clid = o; o += al(4 * Tcap);
     F.o_mk0 = o; o += al(4 * Tcap);
     F.o_mk1 = o; o += al(4 * Tcap);
     F.o_mk2 = o; o += al(4 * Tcap);
-    F.o_clhead = o; o += al(2 * Tcap);
-    F.o_cltail = o; o += al(2 * Tcap);
-    F.o_gscore = o; o += al(8 * Ncap);
-    F.o_gu = o; o += al(4 * Kcap);
-    F.o_gt = o; o += al(2 * Ncap);
-    F.o_gnext = o; o += al(2 * Ncap);
-    F.o_gloc = o; o += al(Ncap);
-    o = std::max(o, lvl0 + al(14 * Kcap + 16));            // the per-locus sort of the prologue is staged from o_hkey on
-    F.Hcap = std::min(65535, (o - lvl0) / 8);              // as are the hits: u32 span + u32 locus mask each
+    F.o_pres = o; o += al(4 * Tcap);
+    F.o_cstart = o; o += al(2 * Tcap);
     F.slice_bytes = o;
+    F.scratch_bytes = 16 * Hcap + 16;
     return o;
 }
 

@@ -71,12 +71,17 @@ class Batch:
             hit_row=cut(self.hit_row, h0, h1), locus_row=cut(self.locus_row, l0, l1))
 
     def sort_hits(self):
-        """The same batch with every contig's hits in descending waafle_score order (ties keep their order).  Semantically
-        transparent -- envelopes are order-free and the annotation tie-break "last hit in file order" (OS:389) is the
-        largest index among equal scores either way -- and it lets the fused fast-path kernel skip its per-locus sort."""
+        """The same batch with every contig's hits in the order the fused fast-path kernel visits them at the first
+        taxonomy level: by (taxon index, descending waafle_score), ties in file order -- the kernel then only CHECKS the
+        order instead of sorting.  Semantically transparent: envelopes are order-free.  With annotation systems the hits
+        are ordered by descending score alone (ties in file order), so that the annotation tie-break "last hit in file
+        order" (OS:389) stays "largest index among equal scores"; the kernel sorts by clade itself."""
         n = self.n_contigs
         contig = np.repeat(np.arange(n, dtype=np.int64), np.diff(self.hit_off))
-        order = np.lexsort((np.arange(len(contig)), -self.hit_score, contig))
+        if self.hit_sysmask is None:
+            order = np.lexsort((np.arange(len(contig)), -self.hit_score, self.hit_taxon, contig))
+        else:
+            order = np.lexsort((np.arange(len(contig)), -self.hit_score, contig))
         take = lambda a: None if a is None else np.ascontiguousarray(a[order])
         return Batch(
             hit_off=self.hit_off, locus_off=self.locus_off,
