@@ -52,6 +52,7 @@ struct wfl_engine {
     // device buffers (grow-only)
     Buf tx[4], anc, in[12], out[18], ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
     Buf fb_list, fast_scratch, fast_wq, blob, status_tmp;
+    size_t fast_scratch_slot = 0;        // bytes of fast-kernel scratch per compute stream
     int plan_nmax = 0;
     int tax_max_depth = 0, anc_rows = 0;
     FastCfg fcfg{}, fcfg2{};            // first pass (all contigs) / second pass (capacity overflows, larger slice)
@@ -537,7 +538,7 @@ void choose_fast_cfg(wfl_engine *e) {
     auto r16 = [](double x) { return (int)((x + 15.0) / 16.0) * 16; };
     const double hq = std::min((double)hmax, e->fast_hscale * hbar);
     const int H = e->fast_hcap ? e->fast_hcap : std::min(16384, std::max(64, r16(hq + 16)));
-    const int M = e->fast_mcap ? e->fast_mcap : std::min(16384, std::max(128, r16(1.06 * H + 16)));
+    const int M = e->fast_mcap ? e->fast_mcap : H;   // entries (hit x locus matches) ~ hits: a few hits match two loci, ~5 % none
     const int T = e->fast_tcap ? e->fast_tcap : std::min(4096, std::max(64, r16(0.42 * H + 16)));
     const int N = e->fast_ncap ? e->fast_ncap : std::min(16384, std::max(96, r16(0.6 * H + 32)));
     fit_layout(e, e->fcfg, H, M, T, N, 64);
@@ -549,7 +550,8 @@ void choose_fast_cfg(wfl_engine *e) {
 
 // One launch of the fused fast-path kernel: pass 0 over the contig range [c0, c0 + n_work), pass 1 over the first
 // pass's capacity overflows (list and count on the device).
-int launch_fast_pass(wfl_engine *e, DevCounters *ctr, int pass, int64_t c0, int64_t n_work, int launch_idx, cudaStream_t stream) {
+int launch_fast_pass(wfl_engine *e, DevCounters *ctr, int pass, int64_t c0, int64_t n_work, int launch_idx, int slot) {
+    cudaStream_t stream = slot ? e->stream2 : e->stream;
     FastArgs a{};
     a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
     a.cfg = pass ? e->fcfg2 : e->fcfg;
@@ -569,10 +571,15 @@ int launch_fast_pass(wfl_engine *e, DevCounters *ctr, int pass, int64_t c0, int6
     a.anc = static_cast<const int *>(e->anc.p);
     a.anc_rows = e->anc_rows;
     a.guard = 1e-12;
+    {
+        int cb = 1;
+        while ((1ll << cb) < (long long)e->tax.n_nodes) ++cb;
+        a.qbits = std::min(32, 48 - cb);
+    }
     a.plan_nmax = e->plan_nmax;
     a.plan_index = static_cast<const PlanEntry *>(e->plan_index.p);
     a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
-    a.scratch = static_cast<char *>(e->fast_scratch.p);
+    a.scratch = static_cast<char *>(e->fast_scratch.p) + (size_t)slot * e->fast_scratch_slot;   // launches on the two streams overlap
     const int wpc = fast_warps_per_cta();
     const int grid = pass ? e->fast_grid2 : (int)std::max<int64_t>(1, std::min<int64_t>(e->fast_grid, (n_work + wpc - 1) / wpc));
     cudaError_t err = launch_fast(a, e->packed, grid, stream);
@@ -647,7 +654,8 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         char *fs;
         if ((rc = outbuf(e, e->fb_list, 2 * ((size_t)e->n + 1), &fb_list))) return rc;
         if ((rc = outbuf(e, e->fast_wq, 256, &fwq))) return rc;
-        if ((rc = outbuf(e, e->fast_scratch, std::max((size_t)e->fast_grid * e->fcfg.scratch_bytes, (size_t)e->fast_grid2 * e->fcfg2.scratch_bytes) * fast_warps_per_cta(), &fs))) return rc;
+        e->fast_scratch_slot = (std::max((size_t)e->fast_grid * e->fcfg.scratch_bytes, (size_t)e->fast_grid2 * e->fcfg2.scratch_bytes) * fast_warps_per_cta() + 255) & ~(size_t)255;
+        if ((rc = outbuf(e, e->fast_scratch, 2 * e->fast_scratch_slot, &fs))) return rc;
         CU(cudaMemsetAsync(fwq, 0, 256 * sizeof(unsigned long long), e->stream));
     }
     CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
@@ -671,7 +679,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
             if (streamed && e->chunks_streamed) CU(cudaStreamWaitEvent(st, e->chunk_ev[k], 0));
             if (use_fast) {
                 if (k >= 250) { set_err(e, "too many chunks"); return WFL_ERR_ARG; }
-                if ((rc = launch_fast_pass(e, ctr, 0, c0, c1 - c0, (int)k, st))) return rc;
+                if ((rc = launch_fast_pass(e, ctr, 0, c0, c1 - c0, (int)k, slot))) return rc;
             } else {
                 if ((rc = launch_pipeline(e, ctr, nullptr, c0, c1 - c0, (size_t)(e->h_hit_off[c1] - e->h_hit_off[c0]), slot, 1))) return rc;
             }
@@ -682,7 +690,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         }
         // second pass: the contigs that overflowed a capacity of the first pass's slice, with a larger slice (their list
         // and count are on the device: no host round trip)
-        if (use_fast && e->fast_passes > 1 && (rc = launch_fast_pass(e, ctr, 1, 0, 0, 255, e->stream))) return rc;
+        if (use_fast && e->fast_passes > 1 && (rc = launch_fast_pass(e, ctr, 1, 0, 0, 255, 0))) return rc;
     }
     CU(cudaEventRecord(e->ev[2], e->stream));
     trace("kernels launched");

@@ -94,7 +94,9 @@ struct FastCfg {
     int o_stat, o_llo, o_llen, o_lraw, o_lstr, o_lbase, o_lcur, o_llast, o_maxb, o_unk;
     int o_hv, o_hsp, o_hcl, o_hid, o_hloc;
     int o_rec, o_gstart, o_gt, o_gloc, o_x;
-    int o_row;     // gene scores in clade-major CSR order; the sort permutation (u16[Pcap]) lives here until they are written
+    int o_row;     // gene scores in clade-major CSR order
+    int o_hp;      // sort permutation of the entries (u16[Pcap])
+    int sort_bytes;   // bytes from o_x to the end of the rows: key array of the per-level sort
     int o_clid, o_mk0, o_mk1, o_mk2, o_pres, o_cstart;
 };
 
@@ -116,6 +118,7 @@ struct FastArgs {
     const int *anc;                // [anc_rows][n_nodes]: l-th ancestor of every node (row 0 = identity)
     int anc_rows;
     double guard;                  // guard band of the decision compares (1e-12)
+    int qbits;                     // score bits in the keys of the per-level sort: 48 - bits(n_nodes), at most 32
     int plan_nmax;
     const PlanEntry *plan_index;
     const uint16_t *plan_data;

@@ -41,11 +41,11 @@ namespace wfl {
 
 namespace {
 
-constexpr int FAST_WPC = 4;     // warps (= contigs in flight) per CTA
+constexpr int FAST_WPC = 2;     // warps (= contigs in flight) per CTA
 constexpr int GMAX = 32;        // retained loci per contig: gene bitmasks are one 32-bit word
 constexpr int NONE16 = 0xffff;
 #ifndef WFL_FAST_CPSM
-#define WFL_FAST_CPSM 5         // resident CTAs per SM the kernel is compiled for (register budget)
+#define WFL_FAST_CPSM 10        // resident CTAs per SM the kernel is compiled for (register budget: 96)
 #endif
 
 #define SM(T, off) (reinterpret_cast<T *>(slice + (off)))
@@ -198,6 +198,7 @@ __device__ __noinline__ double group_slow(const FastArgs &a, char *scratch, int 
     int *ra = reinterpret_cast<int *>(scratch), *rb = ra + cap;
     double *rv = reinterpret_cast<double *>(rb + cap);
     int m = 0;
+    bool desc = true;
 #pragma unroll 1
     for (int q = r0; q < lend && m < cap; ++q) {
         const int h = rec[q];
@@ -207,11 +208,12 @@ __device__ __noinline__ double group_slow(const FastArgs &a, char *scratch, int 
         ra[m] = s;
         rb[m] = e;
         rv[m] = hv[h];
+        desc &= m == 0 || rv[m - 1] >= rv[m];
         ++m;
     }
     if (exact) {
         const PlanEntry pe = a.plan_index[n];
-        return group_mean(ra, rb, rv, 0, m, n, true, pe.k8, a.plan_data + pe.off, (int)pe.nleaf);   // descending scores
+        return group_mean(ra, rb, rv, 0, m, n, desc, pe.k8, a.plan_data + pe.off, (int)pe.nleaf);
     }
     double sum = 0.0;
 #pragma unroll 1
@@ -231,16 +233,6 @@ __device__ __noinline__ double group_slow(const FastArgs &a, char *scratch, int 
         if (!dup && mx > 0.0 && nx != 0x7fffffff) sum += mx * (double)(nx - e);
     }
     return sum / (double)n;
-}
-
-// (clade ascending, score descending, staged index ascending) order of two staged hits; NONE16 pads sort last
-__device__ __forceinline__ bool hit_after(const int *hcl, const double *hv, int x, int y) {
-    if (x == NONE16 || y == NONE16) return x == NONE16 && y != NONE16;
-    const int cx = hcl[x], cy = hcl[y];
-    if (cx != cy) return cx > cy;
-    const double vx = hv[x], vy = hv[y];
-    if (vx != vy) return vx < vy;
-    return x > y;
 }
 
 struct FOut {
@@ -330,7 +322,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
     u16 *gstart = SM(u16, F.o_gstart), *g_t = SM(u16, F.o_gt);   // (clade, locus) groups: first record, clade handle
     u8 *g_loc = SM(u8, F.o_gloc);
     double *row = SM(double, F.o_row);           // gene scores, clade-major CSR
-    u16 *hp = SM(u16, F.o_row);                  // sort permutation of the staged hits (dead before `row` is written)
+    u16 *hp = SM(u16, F.o_hp);                   // sort permutation of the entries (levels whose order had to be sorted)
     int *cl_id = SM(int, F.o_clid);
     u32 *mk0 = SM(u32, F.o_mk0), *mk1 = SM(u32, F.o_mk1), *mk2 = SM(u32, F.o_mk2), *pres = SM(u32, F.o_pres);
     u16 *cstart = SM(u16, F.o_cstart);
@@ -416,16 +408,28 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     big |= hmin < 0 || hmax > 65535;
                     const u8 fl = hits.flags(h0 + h);
                     if (fl & 1) {   // scov_modified >= --min-scov (:362)
+                        u32 cand = 0;
 #pragma unroll 1
                         for (int i = 0; i < G; ++i) {
-                            const int lmin = l_lo[i], llen = l_len[i], lmax = lmin + llen - 1;
-                            if (lmin > hmax || hmin > lmax) continue;
+                            const int lmin = l_lo[i], lmax = lmin + l_len[i] - 1;
+                            bool ok = !(lmin > hmax || hmin > lmax);
                             if (P.p.stranded) {   // hit.sstrand == locus.strand (:365)
                                 const signed char ls = l_str[i];
-                                if (!((ls == '-' && (fl & 2)) || (ls == '+' && !(fl & 2)))) continue;
+                                ok &= (ls == '-' && (fl & 2)) || (ls == '+' && !(fl & 2));
                             }
-                            if (overlap_ok(hmin, hmax, lmin, lmax, llen, P.p.min_overlap)) mb |= 1u << i;
+                            cand |= (ok ? 1u : 0u) << i;
                         }
+                        mb = cand;
+                    }
+                }
+                {   // calc_overlap >= --min-overlap on the candidates (usually one per hit: the lanes stay converged)
+                    u32 cand = mb;
+#pragma unroll 1
+                    while (cand) {
+                        const int i = __ffs(cand) - 1;
+                        cand &= cand - 1u;
+                        const int lmin = l_lo[i], llen = l_len[i];
+                        if (!overlap_ok(hmin, hmax, lmin, lmin + llen - 1, llen, P.p.min_overlap)) mb &= ~(1u << i);
                     }
                 }
                 // one staged ENTRY per (hit, locus) match, in hit order (a hit is rarely attached to more than one locus)
@@ -526,25 +530,43 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 ident = __all_sync(FULL, ok);
             }
             if (!ident) {
+                // bitonic sort of 64-bit keys  clade | (qmax - quantised score) | entry index  in shared memory (aliasing the
+                // per-level arrays).  The score is quantised to a.qbits bits: entries whose scores collide may come out in the
+                // wrong order -- the gene-score walk checks the true order and sends such a group to the order-free sweep.
                 int Pn = 32;
                 while (Pn < Hs) Pn <<= 1;
+                if (8 * Pn > F.sort_bytes) { fallback = true; reason = 3; break; }
+                u64 *sk = reinterpret_cast<u64 *>(xs);
+                const int qb = a.qbits;
+                const double qs = (double)(1ull << (qb - 1));
+                const u64 qmax = (1ull << qb) - 1ull;
 #pragma unroll 1
-                for (int j = lane; j < Pn; j += 32) hp[j] = (u16)(j < Hs ? j : NONE16);
+                for (int j = lane; j < Pn; j += 32) {
+                    u64 key = ~0ull;
+                    if (j < Hs) {
+                        const double x = hv[j] * qs;
+                        const u64 q = x >= (double)qmax ? qmax : (u64)x;
+                        key = ((u64)(u32)hcl[j] << (qb + 16)) | ((qmax - q) << 16) | (u64)j;
+                    }
+                    sk[j] = key;
+                }
                 __syncwarp();
 #pragma unroll 1
                 for (int k = 2; k <= Pn; k <<= 1) {
 #pragma unroll 1
                     for (int jj = k >> 1; jj > 0; jj >>= 1) {
-#pragma unroll 1
+#pragma unroll 2
                         for (int x = lane; x < (Pn >> 1); x += 32) {
                             const int lo = ((x & ~(jj - 1)) << 1) | (x & (jj - 1)), hi = lo | jj;
-                            const int u = hp[lo], w = hp[hi];
-                            const bool up = (lo & k) == 0;
-                            if (hit_after(hcl, hv, u, w) == up) { hp[lo] = (u16)w; hp[hi] = (u16)u; }
+                            const u64 u = sk[lo], w = sk[hi];
+                            if ((u > w) == ((lo & k) == 0)) { sk[lo] = w; sk[hi] = u; }
                         }
                         __syncwarp();
                     }
                 }
+#pragma unroll 1
+                for (int j = lane; j < Hs; j += 32) hp[j] = (u16)(sk[j] & 0xffffull);
+                __syncwarp();
             }
 
             // ---- clades of the level (runs of equal clade: handles in ascending node index) and, in the same pass,
@@ -687,13 +709,19 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     int h = rec[r0];
                     int ua, ub;
                     hit_slice(hsp[h], lmin, llen, ua, ub);
-                    double sum = hv[h] * (double)(ub - ua);   // the group opens with its best hit
+                    double vprev = hv[h];
+                    double sum = vprev * (double)(ub - ua);   // the group opens with its best hit
 #pragma unroll 1
                     for (int q = r0 + 1; q < lend; ++q) {
-                        if (ua == 0 && ub == llen) break;      // the union covers the gene: nothing can be added
                         h = rec[q];
                         if (hcl[h] != cl) break;
                         const double vp = hv[h];
+                        if (vp > vprev) { cplx = true; break; }   // scores that collided in the quantised sort: order-free sweep
+                        vprev = vp;
+                        if (ua == 0 && ub == llen) {           // the union covers the gene: nothing can be added
+                            if (ident) break;
+                            continue;                          // (after a quantised sort the rest of the order is still checked)
+                        }
                         if (!(vp > 0.0)) break;                // descending: the rest contributes nothing
                         int pa, pb;
                         hit_slice(hsp[h], lmin, llen, pa, pb);
@@ -1113,7 +1141,10 @@ int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, in
     F.o_gt = F.o_gstart + al(2 * Ncap);
     F.o_gloc = F.o_gt + al(2 * Ncap);
     o += al(F.x_bytes);
-    F.o_row = o; o += al(std::max(8 * Ncap, 2 * Pcap));
+    // the rows follow: the key array of the per-level sort (8 B x Pcap) spans both regions
+    F.o_row = o; o += al(std::max(8 * Ncap, 8 * Pcap - al(F.x_bytes)));
+    F.sort_bytes = o - F.o_x;
+    F.o_hp = o; o += al(2 * Pcap);
     F.o_clid = o; o += al(4 * Tcap);
     F.o_mk0 = o; o += al(4 * Tcap);
     F.o_mk1 = o; o += al(4 * Tcap);
