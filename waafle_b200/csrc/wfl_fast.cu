@@ -45,7 +45,8 @@ constexpr int FAST_WPC = 2;     // warps (= contigs in flight) per CTA
 constexpr int GMAX = 32;        // retained loci per contig: gene bitmasks are one 32-bit word
 constexpr int NONE16 = 0xffff;
 #ifndef WFL_FAST_CPSM
-#define WFL_FAST_CPSM 10        // resident CTAs per SM the kernel is compiled for (register budget: 96)
+#define WFL_FAST_CPSM 8         // resident CTAs per SM the kernel is compiled for (register budget: 128; shared memory
+                                // limits the residency before the registers do)
 #endif
 
 #define SM(T, off) (reinterpret_cast<T *>(slice + (off)))
@@ -272,6 +273,11 @@ struct Hits<false> {
     }
     __device__ __forceinline__ int taxon(long long h) const { return b.hit_taxon[h]; }
     __device__ __forceinline__ u32 sysmask(long long h) const { return b.hit_sysmask[h]; }
+    __device__ __forceinline__ void all(long long h, int &q1, int &q2, u32 &fl, int &tx) const {
+        span(h, q1, q2);
+        fl = flags(h);
+        tx = b.hit_taxon[h];
+    }
 };
 template <>
 struct Hits<true> {
@@ -284,6 +290,12 @@ struct Hits<true> {
     }
     __device__ __forceinline__ int taxon(long long h) const { return (int)(b.hit_tax16[h] & 0x3fffu); }
     __device__ __forceinline__ u32 sysmask(long long h) const { return b.hit_sysmask8[h]; }
+    __device__ __forceinline__ void all(long long h, int &q1, int &q2, u32 &fl, int &tx) const {
+        span(h, q1, q2);
+        const u32 w = b.hit_tax16[h];
+        fl = ((w >> 15) & 1u) | (((w >> 14) & 1u) << 1);
+        tx = (int)(w & 0x3fffu);
+    }
 };
 
 }  // namespace
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
     u16 *gstart = SM(u16, F.o_gstart), *g_t = SM(u16, F.o_gt);   // (clade, locus) groups: first record, clade handle
     u8 *g_loc = SM(u8, F.o_gloc);
     double *row = SM(double, F.o_row);           // gene scores, clade-major CSR
-    u16 *hp = SM(u16, F.o_hp);                   // sort permutation of the entries (levels whose order had to be sorted)
+    u16 *hp = SM(u16, F.o_row);                  // sort permutation of the entries (dead before the rows are written)
     int *cl_id = SM(int, F.o_clid);
     u32 *mk0 = SM(u32, F.o_mk0), *mk1 = SM(u32, F.o_mk1), *mk2 = SM(u32, F.o_mk2), *pres = SM(u32, F.o_pres);
     u16 *cstart = SM(u16, F.o_cstart);
@@ -395,18 +407,30 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
         if (!fallback && H > 0 && G > 0) {
             bool big = false, bad = false;
             const int *anc0 = a.anc + (size_t)min(R.lifts, a.anc_rows - 1) * (size_t)tax.n_nodes;
+            // the columns of the NEXT tile of hits are requested before the current one is processed
+            int n_q1 = 0, n_q2 = 0, n_tx = 0;
+            u32 n_fl = 0;
+            double n_sc = 0.0;
+            if (lane < H) {
+                hits.all(h0 + lane, n_q1, n_q2, n_fl, n_tx);
+                n_sc = a.b.hit_score[h0 + lane];
+            }
 #pragma unroll 1
             for (int base = 0; base < H; base += 32) {
                 const int h = base + lane;
+                const int q1 = n_q1, q2 = n_q2, tx = n_tx;
+                const u32 fl = n_fl;
+                const double sc = n_sc;
+                if (h + 32 < H) {
+                    hits.all(h0 + h + 32, n_q1, n_q2, n_fl, n_tx);
+                    n_sc = a.b.hit_score[h0 + h + 32];
+                }
                 u32 mb = 0;
                 int hmin = 0, hmax = 0;
                 if (h < H) {
-                    int q1, q2;
-                    hits.span(h0 + h, q1, q2);
                     hmin = min(q1, q2);
                     hmax = max(q1, q2);
                     big |= hmin < 0 || hmax > 65535;
-                    const u8 fl = hits.flags(h0 + h);
                     if (fl & 1) {   // scov_modified >= --min-scov (:362)
                         u32 cand = 0;
 #pragma unroll 1
@@ -436,8 +460,6 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 int tot;
                 const int ex = warp_excl_scan(__popc(mb), tot);
                 if (mb) {
-                    const int tx = hits.taxon(h0 + h);
-                    const double sc = a.b.hit_score[h0 + h];
                     int cl = tax.root;
                     if ((u32)tx >= (u32)tax.n_nodes) bad = true;   // malformed input: the exact pipeline reports it
                     else cl = R.lifts ? anc0[tx] : tx;             // row 0 of the ancestor table is the identity
@@ -1141,16 +1163,18 @@ int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, in
     F.o_gt = F.o_gstart + al(2 * Ncap);
     F.o_gloc = F.o_gt + al(2 * Ncap);
     o += al(F.x_bytes);
-    // the rows follow: the key array of the per-level sort (8 B x Pcap) spans both regions
-    F.o_row = o; o += al(std::max(8 * Ncap, 8 * Pcap - al(F.x_bytes)));
-    F.sort_bytes = o - F.o_x;
-    F.o_hp = o; o += al(2 * Pcap);
     F.o_clid = o; o += al(4 * Tcap);
     F.o_mk0 = o; o += al(4 * Tcap);
     F.o_mk1 = o; o += al(4 * Tcap);
     F.o_mk2 = o; o += al(4 * Tcap);
     F.o_pres = o; o += al(4 * Tcap);
     F.o_cstart = o; o += al(2 * Tcap);
+    // the key array of the per-level sort (8 B x Pcap) spans the records / groups and the clade table, all rebuilt after it
+    if (o - F.o_x < 8 * Pcap) o = F.o_x + 8 * Pcap;
+    F.sort_bytes = o - F.o_x;
+    // the rows; until they are written the sort permutation (u16[Pcap]) lives here
+    F.o_row = o; o += al(std::max(8 * Ncap, 2 * Pcap));
+    F.o_hp = F.o_row;
     F.slice_bytes = o;
     F.scratch_bytes = 16 * Hcap + 16;
     return o;
