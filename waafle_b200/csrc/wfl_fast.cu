@@ -78,12 +78,21 @@ struct FLevel {
     const int *cl_par;       // two-clade search with sister penalty: parent of every LISTED clade of the level, else -1
 };
 
-// gene score of clade t at locus i (0 where the clade has no entry, waafle_orgscorer.py:404-405)
-__device__ __forceinline__ double row_at(const FLevel &L, int t, int i) {
-    if (t == L.t_unk) return L.unk_row[i];
-    const u32 p = L.pres[t];
-    return ((p >> i) & 1u) ? L.row[(int)L.cstart[t] + __popc(p & ((1u << i) - 1u))] : 0.0;
-}
+// gene-score row of one clade: score at locus i, 0 where the clade has no entry (waafle_orgscorer.py:404-405)
+struct RowRef {
+    u32 p;
+    int c;
+    bool dense;
+    __device__ __forceinline__ void open(const FLevel &L, int t) {
+        dense = t == L.t_unk;
+        p = dense ? 0u : L.pres[t];
+        c = dense ? 0 : (int)L.cstart[t];
+    }
+    __device__ __forceinline__ double at(const FLevel &L, int i) const {
+        if (dense) return L.unk_row[i];
+        return ((p >> i) & 1u) ? L.row[c + __popc(p & ((1u << i) - 1u))] : 0.0;
+    }
+};
 
 // Contig.score (waafle_orgscorer.py:447-461) over the non-ignored loci: crit = min, rank = np.mean (n <= 32 values:
 // numpy sums n < 8 sequentially, otherwise eight strided accumulators, the fixed tree, then the tail).
@@ -94,12 +103,15 @@ __device__ __noinline__ double row_stats(const FLevel &L, int t1, int t2, double
     u32 bits = L.um;
     const int body = n < 8 ? 0 : (n & ~7);
     int idx = 0;
+    RowRef w1, w2;
+    w1.open(L, t1);
+    w2.open(L, t2 >= 0 ? t2 : t1);
 #pragma unroll 1
     while (bits) {
         const int i = __ffs(bits) - 1;
         bits &= bits - 1;
-        double v = row_at(L, t1, i);
-        if (t2 >= 0) v = fmax(v, row_at(L, t2, i));
+        double v = w1.at(L, i);
+        if (t2 >= 0) v = fmax(v, w2.at(L, i));
         crit = fmin(crit, v);
         if (idx < body) {
             const int j = idx & 7;
@@ -168,20 +180,26 @@ __device__ __noinline__ void eval_two_fast(const FLevel &L, const DevTax &tax, c
         const int lc = ev.dir ? tax.leaf_count[ev.c2] : min(tax.leaf_count[ev.c1], tax.leaf_count[ev.c2]);
         if (lc < P.p.clade_leaves) ok = false;
     }
-    if (P.p.sister_penalty != 0 && ok) {
-        const int p1 = tax.parent[ev.c1], p2 = tax.parent[ev.c2];
+    ev.ok = ok;   // the sister penalty is checked by the whole warp (sister_hit_warp)
+}
+
+// check_sister_penalty (waafle_orgscorer.py:717-744) for one option, all lanes together over the level's clades: is a B
+// locus claimed by a sister of clade1, or (unless the direction is known) an A locus by a sister of clade2?
+__device__ __noinline__ bool sister_hit_warp(const FLevel &L, const DevTax &tax, const DevParams &P, int t1, int t2, int c1, int c2,
+                                             bool dir, u32 A, u32 B) {
+    const u32 *msis = L.mk[P.sis_sel];
+    const int p1 = tax.parent[c1], p2 = tax.parent[c2];
+    bool hit = false;
 #pragma unroll 1
-        for (int t = 0; t < L.T && ok; ++t) {
-            if (t == ev.t1 || t == ev.t2) continue;
-            const int px = L.cl_par[t];   // get_sisters works on the taxonomy file's rows
-            const bool s1 = px == p1, s2 = (px == p2) && !ev.dir;
-            if (!s1 && !s2) continue;
-            const u32 ms = msis[t];
-            // a B locus is penalised by clade1's sisters, an A locus by clade2's
-            if ((s1 && (ms & B)) || (s2 && (ms & A))) ok = false;
-        }
+    for (int t = lane_id(); t < L.T; t += 32) {
+        if (t == t1 || t == t2) continue;
+        const int px = L.cl_par[t];   // get_sisters works on the taxonomy file's rows
+        const bool s1 = px == p1, s2 = (px == p2) && !dir;
+        if (!s1 && !s2) continue;
+        const u32 ms = msis[t];
+        if ((s1 && (ms & B)) || (s2 && (ms & A))) hit = true;
     }
-    ev.ok = ok;
+    return __any_sync(FULL, hit);
 }
 
 // python slice [h1 : h2+1] of the locus' site array covered by a hit (waafle_orgscorer.py:373-382), for overlapping
@@ -457,8 +475,14 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     }
                 }
                 // one staged ENTRY per (hit, locus) match, in hit order (a hit is rarely attached to more than one locus)
-                int tot;
-                const int ex = warp_excl_scan(__popc(mb), tot);
+                int tot, ex;
+                if (__all_sync(FULL, (mb & (mb - 1u)) == 0u)) {
+                    const u32 att = __ballot_sync(FULL, mb != 0u);
+                    ex = __popc(att & lt_mask());
+                    tot = __popc(att);
+                } else {
+                    ex = warp_excl_scan(__popc(mb), tot);
+                }
                 if (mb) {
                     int cl = tax.root;
                     if ((u32)tx >= (u32)tax.n_nodes) bad = true;   // malformed input: the exact pipeline reports it
@@ -830,11 +854,13 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 u64 bbits = 0;
                 int bid = -1, btl = -1;
                 double bcrit = 0.0;
+                double *rcache = reinterpret_cast<double *>(xs + 4 * F.Tcap);   // after the kept-clade list
 #pragma unroll 1
                 for (int t = lane; t < T; t += 32) {
                     if ((mk0[t] & um) != um) continue;   // crit >= k1
                     double crit;
                     const double rank = row_stats(L, t, -1, &crit);
+                    rcache[t] = rank;   // for the meld pass
                     const u64 b = dbits(rank);
                     if (b > bbits || (b == bbits && cl_id[t] > bid)) { bbits = b; bid = cl_id[t]; btl = t; bcrit = crit; }
                 }
@@ -856,9 +882,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         const int t = base + lane;
                         bool kept = false;
                         if (t < T && (mk0[t] & um) == um) {
-                            double crit;
-                            const double rank = t == tb ? brank : row_stats(L, t, -1, &crit);
-                            const double d = brank - rank;
+                            const double d = brank - rcache[t];
                             if (t != tb && fabs(d) <= GUARD) near = true;
                             if (P.p.disambiguate_one == 1 && fabs(d - P.p.range) <= GUARD) near = true;
                             kept = P.p.disambiguate_one == 1 && d <= P.p.range;
@@ -983,6 +1007,8 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     const int bi = s_a[bp], bj = s_b[bp];
                     FTwoEval be;
                     eval_two_fast(L, tax, P, bi, bj, be);
+                    if (P.p.sister_penalty != 0 && be.ok && sister_hit_warp(L, tax, P, be.t1, be.t2, be.c1, be.c2, be.dir, be.A, be.B))
+                        be.ok = false;
                     double bcrit;
                     const double brank = row_stats(L, bi, bj, &bcrit);
                     // meld_two (:633-669) over the options within --range
@@ -992,20 +1018,43 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     int nk = 0, nbad = 0, ndiff = 0, la = -1, lb = -1;
                     bool near = false;
 #pragma unroll 1
-                    for (int q = lane; q < nsurv; q += 32) {
-                        const double d = brank - s_rank[q];
-                        if (q != bp && fabs(d) <= GUARD) near = true;
-                        if (P.p.disambiguate_two != 0 && fabs(d - P.p.range) <= GUARD) near = true;
-                        if (!(d <= P.p.range)) continue;   // :636
+                    for (int qb = 0; qb < nsurv; qb += 32) {
+                        const int q = qb + lane;
+                        bool kept = false;
                         FTwoEval ev;
-                        eval_two_fast(L, tax, P, s_a[q], s_b[q], ev);
-                        ++nk;
-                        nbad += !ev.ok;
-                        ndiff += !(ev.A == be.A && ev.B == be.B && ev.amb == be.amb);   // meld_precheck (:671-676)
-                        la = lca2(tax, la, ev.c1);
-                        lb = lca2(tax, lb, ev.c2);
-                        memA[ev.t1] = 1;
-                        memB[ev.t2] = 1;
+                        ev.ok = true;
+                        ev.t1 = ev.t2 = ev.c1 = ev.c2 = 0;
+                        ev.A = ev.B = 0u;
+                        ev.dir = false;
+                        if (q < nsurv) {
+                            const double d = brank - s_rank[q];
+                            if (q != bp && fabs(d) <= GUARD) near = true;
+                            if (P.p.disambiguate_two != 0 && fabs(d - P.p.range) <= GUARD) near = true;
+                            kept = d <= P.p.range;   // :636
+                            if (kept) eval_two_fast(L, tax, P, s_a[q], s_b[q], ev);
+                        }
+                        if (P.p.sister_penalty != 0) {   // one kept option at a time, all lanes over the clades
+                            u32 pend = __ballot_sync(FULL, kept && ev.ok);
+#pragma unroll 1
+                            while (pend) {
+                                const int src = __ffs(pend) - 1;
+                                pend &= pend - 1;
+                                const bool hit = sister_hit_warp(L, tax, P, __shfl_sync(FULL, ev.t1, src), __shfl_sync(FULL, ev.t2, src),
+                                                                 __shfl_sync(FULL, ev.c1, src), __shfl_sync(FULL, ev.c2, src),
+                                                                 __shfl_sync(FULL, (int)ev.dir, src) != 0, __shfl_sync(FULL, ev.A, src),
+                                                                 __shfl_sync(FULL, ev.B, src));
+                                if (lane == src && hit) ev.ok = false;
+                            }
+                        }
+                        if (kept) {
+                            ++nk;
+                            nbad += !ev.ok;
+                            ndiff += !(ev.A == be.A && ev.B == be.B && ev.amb == be.amb);   // meld_precheck (:671-676)
+                            la = lca2(tax, la, ev.c1);
+                            lb = lca2(tax, lb, ev.c2);
+                            memA[ev.t1] = 1;
+                            memB[ev.t2] = 1;
+                        }
                     }
                     if (__any_sync(FULL, near)) { trip = true; break; }
                     nk = warp_sum(nk);
@@ -1157,7 +1206,7 @@ int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, in
     //   two-clade: candidates (Tcap u16) | clade parents (Tcap int) | member flags (2 x Tcap u8) | survivors (12 B each)
     //   one-clade: kept clades (Tcap int)
     const int per_level = al(2 * Mcap) + al(2 * Ncap) + al(2 * Ncap) + al(Ncap);
-    F.x_bytes = std::max(per_level, al(2 * Tcap) + 4 * Tcap + 2 * al(Tcap) + 12 * F.Scap + 16);
+    F.x_bytes = std::max(std::max(per_level, 12 * Tcap + 16), al(2 * Tcap) + 4 * Tcap + 2 * al(Tcap) + 12 * F.Scap + 16);
     F.o_rec = F.o_x = o;
     F.o_gstart = F.o_rec + al(2 * Mcap);
     F.o_gt = F.o_gstart + al(2 * Ncap);
