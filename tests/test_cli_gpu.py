@@ -43,3 +43,45 @@ def test_cli_reproduces_shipped_demo_tsvs(tmp_path, prodigal):
         with open(os.path.join(str(outs["one"]), "run.{}.tsv".format(kind))) as f1, \
                 open(os.path.join(str(outs["chunked"]), "run.{}.tsv".format(kind))) as f2:
             assert f1.read() == f2.read(), kind
+
+
+def run_cli(files, outdir, extra):
+    from waafle_b200 import orgscorer
+    os.makedirs(str(outdir), exist_ok=True)
+    orgscorer.main([files["contigs"], files["blastout"], files["gff"], files["taxonomy"],
+                    "--outdir", str(outdir), "--basename", "demo_contigs", "--quiet"] + extra)
+    return {kind: open(os.path.join(str(outdir), "demo_contigs.{}.tsv".format(kind))).read()
+            for kind in ("lgt", "no_lgt", "unclassified")}
+
+
+@pytest.mark.parametrize("gff", ["genecaller", "prodigal"])
+def test_cli_bytes_equal_reference_cli(tmp_path, gff):
+    """TSV bytes of the drop-in CLI == bytes the CURRENT unmodified reference CLI writes (tests/golden/demo_cli, made by
+    tests/golden/make_golden_tsv.py) for the demo under default and non-default flags; fast path and exact pipeline."""
+    import json
+    root = os.path.join(helpers.GOLDEN, "demo_cli")
+    flag_sets = json.load(open(os.path.join(root, "flag_sets.json")))
+    files = helpers.demo_files(tmp_path, gff == "prodigal")
+    for k, flags in enumerate(flag_sets):
+        want = {kind: open(os.path.join(root, "{}_{}".format(gff, k), "demo_contigs.{}.tsv".format(kind))).read()
+                for kind in ("lgt", "no_lgt", "unclassified")}
+        for tag, extra in (("fast", []), ("exact", ["--exact-scores"]), ("stream", ["--stream-mb", "0.004", "--devices", "0,0"])):
+            got = run_cli(files, tmp_path / "{}_{}".format(tag, k), flags + extra)
+            for kind in want:
+                assert got[kind] == want[kind], (gff, flags, tag, kind)
+
+
+def test_streamed_two_workers_equal_single_call_on_synthetic(tmp_path):
+    """BASELINE configs[4] shape (Prodigal-style loci, annotation transfer, --weak-loci) as text files: the streamed run
+    (contig-aligned chunks, two worker processes, GPU parser, per-chunk shards, k-way merge) writes the same bytes as
+    the single call, under each --weak-loci mode."""
+    from waafle_b200 import synth
+    data = synth.generate_config("cfg5", n_contigs=1500, seed=401, annotations=True)
+    files = data.write_files(str(tmp_path), "demo_contigs")
+    with open(files["contigs"], "a") as fh:
+        fh.write(">zzz_no_hits\nACGTACGTAC\n")
+    for mode in ("ignore", "penalize", "assign-unknown"):
+        one = run_cli(files, tmp_path / ("one_" + mode), ["--weak-loci", mode])
+        two = run_cli(files, tmp_path / ("two_" + mode), ["--weak-loci", mode, "--stream-mb", "2", "--devices", "0,0"])
+        assert one == two, mode
+        assert one["no_lgt"].count("\n") > 100

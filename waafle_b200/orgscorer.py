@@ -60,7 +60,33 @@ def get_args(argv=None):
                    help="parse the blastout with the CPU reader instead of the CUDA parser")
     g.add_argument("--chunk-contigs", type=int, default=250000,
                    help="contigs per engine call (streaming; results are merged) [default: 250000]")
+    g.add_argument("--exact-scores", action="store_true",
+                   help="score every contig with the exact (numpy summation order) pipeline: min/avg scores bit-identical to\n"
+                        "the reference instead of within 1e-12 [default: fused fast path with guard bands]")
+    g.add_argument("--devices", default=None, metavar="<0,1,...|all>",
+                   help="CUDA devices for a streamed run: the blastout is cut into contig-aligned chunks that are parsed,\n"
+                        "scored and written by one worker process per device, then merged by contig name\n"
+                        "[default: the single --device, whole file in one pass]")
+    g.add_argument("--stream-mb", type=float, default=0.0, metavar="<MB>",
+                   help="blastout text per streamed chunk; > 0 streams even on one device [default: 256 with --devices]")
     return parser.parse_args(argv)
+
+
+def device_list(spec, default):
+    """`--devices` -> list of CUDA device indices, without touching CUDA in this process (the workers are forks)."""
+    if spec is None:
+        return [default]
+    if spec == "all":
+        import subprocess
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        n = sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+        if n == 0:
+            die("--devices all: nvidia-smi lists no GPU")
+        return list(range(n))
+    try:
+        return [int(x) for x in spec.split(",") if x != ""]
+    except ValueError:
+        die("bad --devices:", spec)
 
 
 def score_in_chunks(engine, batch, chunk):
@@ -107,6 +133,20 @@ def main(argv=None):
     if args.basename is None:
         args.basename = os.path.split(args.contigs)[1].split(".")[0]
     say("Analyzing contigs.")
+    if args.devices is not None or args.stream_mb > 0:
+        from . import streaming
+        devices = device_list(args.devices, args.device)
+        chunk_bytes = int((args.stream_mb if args.stream_mb > 0 else 256.0) * (1 << 20))
+        stats, n_chunks = streaming.run_streaming(
+            args, tax, contig_lengths, loci, lambda n_sys: OrgscorerParams.from_args(args, n_systems=n_sys),
+            devices, max(1, chunk_bytes))
+        if not args.quiet:
+            for dev in sorted(k for k in stats if k != "rest"):
+                st = stats[dev]
+                say("  cuda:{}: {:,} contigs / {:,} hits in {} chunk(s) ({:.1f} ms in kernels)".format(
+                    dev, st["contigs"], st["hits"], st["chunks"], st["ms_kernels"]))
+        say("Finished successfully.")
+        return
     hits = parsers.read_blast_hits(args.blastout, device=None if args.cpu_parse else args.device)
     if hits.sysmask is None:
         die("more than 32 annotation systems in the subject headers")
@@ -114,6 +154,8 @@ def main(argv=None):
     batch = packing.pack(contig_lengths, loci, hits, tax)
     params = OrgscorerParams.from_args(args, n_systems=len(hits.systems))
     engine = Engine(args.device, params, tax)
+    if args.exact_scores:
+        engine.set_option("exact", 1)
     res = score_in_chunks(engine, batch, args.chunk_contigs)
     if not args.quiet:
         st = engine.stats()

@@ -245,14 +245,16 @@ def merge_shards(prefixes, outdir, basename, remove=True):
 class ChunkScorer:
     """Everything one device needs to turn a piece of blastout text into shard rows."""
 
-    def __init__(self, device, args, tax, contig_lengths, loci_index, params_factory, cpu_parse=False):
-        from .engine import Engine
+    def __init__(self, device, args, tax, contig_lengths, loci_index, params_factory, cpu_parse=False, engine_factory=None):
+        if engine_factory is None:
+            from .engine import Engine
+            engine_factory = Engine
         self.device, self.args, self.tax = device, args, tax
         self.contig_lengths, self.loci_index = contig_lengths, loci_index
         self.params_factory = params_factory
         self.cpu_parse = cpu_parse
         self.engine = None
-        self.Engine = Engine
+        self.Engine = engine_factory   # (device, params, taxonomy) -> object with score_batch / set_params / set_taxonomy / stats / close
         self.parser = None
         self.known_taxa = set()
         self.n_systems = None
@@ -290,6 +292,8 @@ class ChunkScorer:
         n_sys = len(hits.systems)
         if self.engine is None:
             self.engine = self.Engine(self.device, self.params_factory(n_sys), self.tax)
+            if getattr(self.args, "exact_scores", False):
+                self.engine.set_option("exact", 1)
         else:
             if n_sys != self.n_systems:
                 self.engine.set_params(self.params_factory(n_sys))
