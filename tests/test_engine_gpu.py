@@ -1,9 +1,11 @@
 """GPU parity tests proper: the CUDA engine, called through the C ABI, against the oracle.
 
 Two modes, both run by every comparison helper here:
-  * default (fused fast-path kernel with guard bands, exact pipeline for what it hands back): every integer / byte /
-    index output bit-exact, crit and rank within SCORE_RTOL = 1e-12 relative (BASELINE.json north_star tolerance);
-  * exact (`set_option("exact", 1)`, the numpy-pairwise pipeline): crit and rank bit-exact as well.
+  * default (fused fast-path kernel with guard bands on its decisions and on the 4-decimal print edge of the scores it
+    reports; exact pipeline for what it hands back): every integer / byte / index output bit-exact, crit and rank
+    within SCORE_RTOL = 1e-12 relative (BASELINE.json north_star tolerance) -- and the TSV bytes identical
+    (tests/test_cli_gpu.py);
+  * exact (`set_option("exact", 1)`, the numpy-pairwise pipeline for every contig): crit and rank bit-exact as well.
 """
 import numpy as np
 import pytest

@@ -254,6 +254,71 @@ __device__ __noinline__ double group_slow(const FastArgs &a, char *scratch, int 
     return sum / (double)n;
 }
 
+// The writer prints the scores a contig reports (crit / rank of the chosen clade or pair, waafle_orgscorer.py:447-461) with
+// four decimals (utils.py:137-139).  A fast-path score is within ~1e-14 of the reference's; when it lies within 1e-11 of a
+// value that prints differently on either side (x.xxxx5 -- systematic for 3-decimal pident values), the gene scores of the
+// chosen clade(s) -- at most one group per locus -- are recomputed in numpy's summation order, one lane per locus, and
+// written back into the rows; the caller then re-runs row_stats, so the TSV bytes equal the reference's.
+__device__ __forceinline__ bool near_print_edge(double v) {
+    const double x = v * 1e4;
+    return fabs(x - floor(x) - 0.5) <= 1e-7;
+}
+// rows_exact: exact gene scores of clade t, lane per locus.  Records of a
+// locus are sorted by (clade, score descending): the group is found by binary search.  Groups of more than LC records go
+// through the warp's global scratch, one at a time.
+constexpr int LC = 24;
+__device__ __noinline__ void rows_exact(const FastArgs &a, char *cold, int coldcap, const FLevel &L, double *row, int t, int lane, int G,
+                                        const u16 *l_base, const int *l_lo, const u16 *rec, const u32 *hsp, const int *hcl,
+                                        const double *hv) {
+    if (t == L.t_unk) return;   // (dense row: the caller does not report it from here)
+    const u32 pm = L.pres[t];
+    const int clade = L.cl_id[t];
+    const bool act = lane < G && ((pm >> lane) & 1u);
+    bool big = false;
+    int r0 = 0, lend = 0, lmin = 0, n = 1;
+    double sc = 0.0;
+    if (act) {
+        int lo = l_base[lane], hi = l_base[lane + 1];
+        lend = hi;
+        lmin = l_lo[lane];
+        n = L.l_len[lane];
+#pragma unroll 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (hcl[rec[mid]] < clade) lo = mid + 1; else hi = mid;
+        }
+        r0 = lo;
+        int ra[LC], rb[LC];
+        double rv[LC];
+        int m = 0;
+        bool desc = true;
+#pragma unroll 1
+        for (int q = r0; q < lend; ++q) {
+            const int h = rec[q];
+            if (hcl[h] != clade) break;
+            if (m == LC) { big = true; break; }
+            hit_slice(hsp[h], lmin, n, ra[m], rb[m]);
+            rv[m] = hv[h];
+            desc &= m == 0 || rv[m - 1] >= rv[m];
+            ++m;
+        }
+        if (!big) {
+            const PlanEntry pe = a.plan_index[n];
+            sc = group_mean(ra, rb, rv, 0, m, n, desc, pe.k8, a.plan_data + pe.off, (int)pe.nleaf);
+        }
+    }
+    u32 bm = __ballot_sync(FULL, act && big);
+#pragma unroll 1
+    while (bm) {
+        const int ln = __ffs(bm) - 1;
+        bm &= bm - 1;
+        if (lane == ln) sc = group_slow(a, cold, coldcap, rec, hsp, hcl, hv, r0, lend, clade, lmin, n, true);
+        __syncwarp();
+    }
+    if (act) row[(int)L.cstart[t] + __popc(pm & ((1u << lane) - 1u))] = sc;
+    __syncwarp();
+}
+
 struct FOut {
     int call, dir, c1, c2, lca, b1, b2, na, nb, lifts;
     long long mem;
@@ -356,7 +421,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
     int *cl_id = SM(int, F.o_clid);
     u32 *mk0 = SM(u32, F.o_mk0), *mk1 = SM(u32, F.o_mk1), *mk2 = SM(u32, F.o_mk2), *pres = SM(u32, F.o_pres);
     u16 *cstart = SM(u16, F.o_cstart);
-    char *xs = SM(char, F.o_x);                  // search scratch (aliases rec / gstart / g_t / g_loc)
+    char *xs = SM(char, F.o_x);                  // search scratch (aliases gstart / g_t / g_loc)
     unsigned long long *stat = SM(unsigned long long, F.o_stat);   // per-warp counters, flushed once at exit
     char *gscr = a.scratch + ((size_t)blockIdx.x * FAST_WPC + wid) * (size_t)F.scratch_bytes;
     char *cold = gscr;                           // record arrays of the cold gene-score paths
@@ -582,7 +647,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                 int Pn = 32;
                 while (Pn < Hs) Pn <<= 1;
                 if (8 * Pn > F.sort_bytes) { fallback = true; reason = 3; break; }
-                u64 *sk = reinterpret_cast<u64 *>(xs);
+                u64 *sk = reinterpret_cast<u64 *>(rec);
                 const int qb = a.qbits;
                 const double qs = (double)(1ull << (qb - 1));
                 const u64 qmax = (1ull << qb) - 1ull;
@@ -871,7 +936,6 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     const int owner = __ffs(__ballot_sync(FULL, bbits == wb && (long long)bid == wid2)) - 1;
                     const int tb = __shfl_sync(FULL, btl, owner);
                     const double brank = dbits_inv(wb);
-                    const double bcr = __shfl_sync(FULL, bcrit, owner);
                     // meld_one (:621-631): options within --range of the best; guard the arg-max and the range edge
                     int my = -1, nk = 0;
                     bool near = false;
@@ -896,10 +960,18 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         kbase += __popc(m);
                     }
                     if (__any_sync(FULL, near)) { trip = true; break; }
+                    R.crit = __shfl_sync(FULL, bcrit, owner);
+                    R.rank = brank;
+                    if (near_print_edge(R.crit) || near_print_edge(R.rank)) {
+                        // a reported score the writer would round the other way if it were 1e-12 off: recompute the clade's
+                        // gene scores in numpy's summation order (the dense Unknown row: exact pipeline)
+                        if (tb == t_unk) { trip = true; break; }
+                        rows_exact(a, cold, F.Hcap, L, row, tb, lane, G, l_base, l_lo, rec, hsp, hcl, hv);
+                        R.rank = row_stats(L, tb, -1, &R.crit);
+                        if (lane == 0) ++stat[ST_REFINED];
+                    }
                     R.call = WFL_CALL_NO_LGT;
                     R.b1 = R.c1 = cl_id[tb];
-                    R.crit = bcr;
-                    R.rank = brank;
                     if (P.p.disambiguate_one == 1) {
                         R.c1 = warp_lca(tax, my);
                         R.na = warp_sum(nk);
@@ -1080,14 +1152,21 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         }
                     }
                     if (have && be.ok) {
+                        R.crit = bcrit;
+                        R.rank = brank;
+                        if (near_print_edge(bcrit) || near_print_edge(brank)) {   // see the one-clade search
+                            if (be.t1 == t_unk || be.t2 == t_unk) { trip = true; break; }
+                            rows_exact(a, cold, F.Hcap, L, row, be.t1, lane, G, l_base, l_lo, rec, hsp, hcl, hv);
+                            rows_exact(a, cold, F.Hcap, L, row, be.t2, lane, G, l_base, l_lo, rec, hsp, hcl, hv);
+                            R.rank = row_stats(L, be.t1, be.t2, &R.crit);
+                            if (lane == 0) ++stat[ST_REFINED];
+                        }
                         R.call = WFL_CALL_LGT;
                         R.b1 = be.c1;
                         R.b2 = be.c2;
                         R.c1 = c1;
                         R.c2 = c2;
                         R.lca = lca2(tax, c1, c2);   // waafle_orgscorer.py:882
-                        R.crit = bcrit;
-                        R.rank = brank;
                         R.dir = be.dir;
                         if (lane < G) {
                             const u32 m = 1u << lane;
@@ -1202,13 +1281,14 @@ int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, in
     F.o_hcl = o; o += al(4 * Hcap);
     F.o_hid = o; o += n_systems > 0 ? al(2 * Hcap) : 0;
     F.o_hloc = o; o += al(Hcap);
-    // per-level records and groups; the search scratch aliases them (dead once the gene scores are written):
+    // per-level records, then the groups; the search scratch aliases the groups (dead once the gene scores are written):
     //   two-clade: candidates (Tcap u16) | clade parents (Tcap int) | member flags (2 x Tcap u8) | survivors (12 B each)
-    //   one-clade: kept clades (Tcap int)
-    const int per_level = al(2 * Mcap) + al(2 * Ncap) + al(2 * Ncap) + al(Ncap);
-    F.x_bytes = std::max(std::max(per_level, 12 * Tcap + 16), al(2 * Tcap) + 4 * Tcap + 2 * al(Tcap) + 12 * F.Scap + 16);
-    F.o_rec = F.o_x = o;
-    F.o_gstart = F.o_rec + al(2 * Mcap);
+    //   one-clade: kept clades (Tcap int) | ranks (Tcap double)
+    F.o_rec = o; o += al(2 * Mcap);
+    const int groups = al(2 * Ncap) + al(2 * Ncap) + al(Ncap);
+    F.x_bytes = std::max(std::max(groups, 12 * Tcap + 16), al(2 * Tcap) + 4 * Tcap + 2 * al(Tcap) + 12 * F.Scap + 16);
+    F.o_x = o;
+    F.o_gstart = o;
     F.o_gt = F.o_gstart + al(2 * Ncap);
     F.o_gloc = F.o_gt + al(2 * Ncap);
     o += al(F.x_bytes);
@@ -1219,8 +1299,8 @@ int fast_layout(FastCfg &F, int Hcap, int Mcap, int Tcap, int Ncap, int Scap, in
     F.o_pres = o; o += al(4 * Tcap);
     F.o_cstart = o; o += al(2 * Tcap);
     // the key array of the per-level sort (8 B x Pcap) spans the records / groups and the clade table, all rebuilt after it
-    if (o - F.o_x < 8 * Pcap) o = F.o_x + 8 * Pcap;
-    F.sort_bytes = o - F.o_x;
+    if (o - F.o_rec < 8 * Pcap) o = F.o_rec + 8 * Pcap;
+    F.sort_bytes = o - F.o_rec;
     // the rows; until they are written the sort permutation (u16[Pcap]) lives here
     F.o_row = o; o += al(std::max(8 * Ncap, 2 * Pcap));
     F.o_hp = F.o_row;

@@ -29,6 +29,16 @@ EXPORTS = ["wfl_abi_version", "wfl_device_count", "wfl_create", "wfl_destroy", "
            "wfl_host_free", "wfl_parser_create", "wfl_parser_destroy", "wfl_parser_last_error", "wfl_parse_blast",
            "wfl_parse_distinct", "wfl_parse_fetch", "wfl_parser_times"]
 ABI_VERSION = 2
+_CUDA_TOUCHED = False   # this process has initialised CUDA through the library (a fork could not use it any more)
+
+
+def mark_cuda_touched():
+    global _CUDA_TOUCHED
+    _CUDA_TOUCHED = True
+
+
+def cuda_touched():
+    return _CUDA_TOUCHED
 PACKED_MAX_NODES, PACKED_MAX_COORD, PACKED_MAX_SYSTEMS = 16384, 65535, 8
 
 
@@ -172,6 +182,7 @@ class Engine:
         if self._lib.wfl_abi_version() != ABI_VERSION:
             raise EngineError("ABI version mismatch")
         h = ctypes.c_void_p()
+        mark_cuda_touched()
         rc = self._lib.wfl_create(int(device), ctypes.byref(h))
         if rc != 0 or not h:
             raise EngineError("wfl_create(device={}) failed with {}: no usable CUDA device "

@@ -12,7 +12,7 @@ import ctypes
 
 import numpy as np
 
-from .engine import EngineError, load_library
+from .engine import EngineError, load_library, mark_cuda_touched
 
 TAX_SLOTS, SYS_SLOTS = 1 << 20, 64
 _ready = False
@@ -58,6 +58,7 @@ class BlastParser:
     def __init__(self, device=0):
         self._lib = _lib()
         h = ctypes.c_void_p()
+        mark_cuda_touched()
         rc = self._lib.wfl_parser_create(int(device), ctypes.byref(h))
         if rc != 0 or not h:
             raise EngineError("wfl_parser_create(device={}) failed with {}: no usable CUDA device".format(device, rc))

@@ -8,6 +8,7 @@ output TSVs.  The only part that differs is the body of the major contig loop
 """
 
 import argparse
+import functools
 import os
 import sys
 
@@ -70,6 +71,10 @@ def get_args(argv=None):
     g.add_argument("--stream-mb", type=float, default=0.0, metavar="<MB>",
                    help="blastout text per streamed chunk; > 0 streams even on one device [default: 256 with --devices]")
     return parser.parse_args(argv)
+
+
+def params_from_args(args, n_systems):
+    return OrgscorerParams.from_args(args, n_systems=n_systems)
 
 
 def device_list(spec, default):
@@ -138,7 +143,7 @@ def main(argv=None):
         devices = device_list(args.devices, args.device)
         chunk_bytes = int((args.stream_mb if args.stream_mb > 0 else 256.0) * (1 << 20))
         stats, n_chunks = streaming.run_streaming(
-            args, tax, contig_lengths, loci, lambda n_sys: OrgscorerParams.from_args(args, n_systems=n_sys),
+            args, tax, contig_lengths, loci, functools.partial(params_from_args, args),
             devices, max(1, chunk_bytes))
         if not args.quiet:
             for dev in sorted(k for k in stats if k != "rest"):

@@ -342,15 +342,17 @@ def _worker(device, path, tasks, results, shard_dir, args, tax, contig_lengths, 
 
 
 def run_streaming(args, tax, contig_lengths, loci, params_factory, devices, chunk_bytes):
-    """The whole streamed run: returns per-device stats.  `devices`: CUDA device indices, one worker process each (the
-    parent never initialises CUDA, so the workers are plain forks sharing the contig / loci tables copy-on-write)."""
+    """The whole streamed run: returns per-device stats.  `devices`: CUDA device indices, one worker process each.  The
+    CLI's parent process never initialises CUDA before this point, so the workers are plain forks sharing the contig /
+    loci tables copy-on-write; a caller that already used CUDA in this process gets spawned workers (pickled tables)."""
     import multiprocessing as mp
     import shutil
     import tempfile
+    from . import engine as _engine
     loci_index = LociIndex(loci, contig_lengths)
     chunks = scan_blast_chunks(args.blastout, chunk_bytes) if os.path.getsize(args.blastout) > 0 else []
     shard_dir = tempfile.mkdtemp(prefix="wfl_shards_", dir=args.outdir)
-    ctx = mp.get_context("fork")
+    ctx = mp.get_context("spawn" if _engine.cuda_touched() else "fork")
     tasks, results = ctx.Queue(), ctx.Queue()
     for cid, (off, length) in enumerate(chunks):
         tasks.put((cid, off, length))
