@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[2] strong-scaling leg")
     ap.add_argument("--strong-contigs", type=int, default=1_000_000)
+    ap.add_argument("--no-stream", action="store_true", help="skip the configs[4] streaming leg")
+    ap.add_argument("--stream-contigs", type=int, default=10_000_000)
+    ap.add_argument("--stream-chunk", type=int, default=125_000, help="contigs per streamed chunk")
     ap.add_argument("--exact", action="store_true", help="exact pipeline for every contig (bit-exact crit / rank)")
     ap.add_argument("--wide", action="store_true", help="e2e leg with the wide 29 B/hit wire format")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (wfl_set_option)")
@@ -312,6 +315,25 @@ class E2E:
             self.gather_ms = e0.elapsed_time(e1)
         self.sizes = sizes
 
+    def h2d_ceiling(self, barrier, reps=3):
+        """Pure host->device copies of this rank's pinned wire buffers, all ranks at once: the bandwidth the box gives the
+        plugin call's H2D window (ms per step's bytes, max over ranks is taken by the caller)."""
+        torch = self.torch
+        dst = {k: torch.empty(v.nbytes, dtype=torch.uint8, device="cuda") for k, v in self.harr.items()}
+        src = {k: torch.from_numpy(v.view(np.uint8).reshape(-1)) for k, v in self.harr.items()}
+        best = None
+        for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in dst:
+                dst[k].copy_(src[k], non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+
     def gathered_results(self, hit_bases):
         """rank 0, N > 1: the whole batch's results from the last step's gathered buffers."""
         from waafle_b200 import dist as wdist
@@ -421,6 +443,7 @@ def main():
     e2e_ms = timed_e2e(e2e, args.steps, args.warmup - 1, barrier)
     st_e2e = eng.stats()
     gather_ms = e2e.gather_ms
+    ceil_ms = e2e.h2d_ceiling(barrier)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if world > 1 and rank == 0:
@@ -439,12 +462,16 @@ def main():
         strong = strong_leg(args, eng, dist, world, rank, barrier, rtol)
 
     # ---- max over ranks ----
-    tv = torch.tensor([dev_ms, score_ms, e2e_ms, wall_ms, gather_ms], dtype=torch.float64, device="cuda")
+    stream = None
+    if not args.no_stream and args.workload == "cfg2":
+        stream = stream_leg(args, eng, dist, world, rank, barrier)
+
+    tv = torch.tensor([dev_ms, score_ms, e2e_ms, wall_ms, gather_ms, ceil_ms], dtype=torch.float64, device="cuda")
     hv = torch.tensor([float(h2d_bytes)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
         dist.all_reduce(hv, op=dist.ReduceOp.SUM)
-    dev_ms, score_ms, e2e_ms, wall_ms, gather_ms = tv.tolist()
+    dev_ms, score_ms, e2e_ms, wall_ms, gather_ms, ceil_ms = tv.tolist()
     h2d_total = hv.item()
     n_total = n_base * world
 
@@ -495,6 +522,9 @@ def main():
                     "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "wire_format": wire_format,
                     "h2d_aggregate_gbs": h2d_total / max(st_e2e["ms_h2d"], 1e-6) / 1e6,
+                    "h2d_ceiling": {"ms_per_step_bytes": ceil_ms, "aggregate_gbs": h2d_total / max(ceil_ms, 1e-6) / 1e6,
+                                    "what": "the same pinned buffers copied host->device by all ranks at once with nothing else "
+                                            "running (best of 3, max over ranks): what this box's host side can feed"},
                     "results": "host arrays through wfl_score_batch" if world == 1 else
                                "packed records gathered to rank 0 over NCCL from device buffers, then D2H",
                     "nccl_gather_ms": gather_ms if world > 1 else None,
@@ -508,6 +538,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "parity": parity,
             "strong": strong,
+            "stream": stream,
             "clocks": sampler.summary(),
             "calls": {"lgt": int(res["call_counts"][0]), "no_lgt": int(res["call_counts"][1]),
                       "unclassified": int(res["call_counts"][2])},
@@ -569,6 +600,91 @@ def strong_leg(args, eng, dist, world, rank, barrier, rtol):
                                                "refined_groups", "workspace_retries")}}
     e2e.close()
     return out
+
+
+def stream_leg(args, eng, dist, world, rank, barrier):
+    """configs[4]: `--stream-contigs` Prodigal-style contigs with annotation transfer under --weak-loci assign-unknown,
+    streamed in chunks of `--stream-chunk` contigs; chunk k goes to rank k % N.  Every chunk is a full plugin call from
+    pinned host buffers (H2D + kernels + compaction), its packed result records are read back to the host (what a writer
+    would consume), and the call counts of all chunks are summed over the ranks at the end.  The chunks are tiles of one
+    generated chunk (a 10M-contig synthetic set does not fit a build-time budget); rank 0 checks the chunk against the C
+    restatement under all three --weak-loci modes."""
+    import torch
+    from waafle_b200 import dist as wdist
+    from waafle_b200.engine import PinnedArena
+    from waafle_b200.params import OrgscorerParams
+    from waafle_b200 import synth
+    data = synth.generate_config("cfg5", n_contigs=args.stream_chunk, seed=1000, annotations=True)
+    tax5 = data.taxonomy()
+    chunk = data.to_batch(tax5).sort_hits()
+    n_chunks = max(1, (args.stream_contigs + chunk.n_contigs - 1) // chunk.n_contigs)
+    mine = len(range(rank, n_chunks, world))
+    modes = ("assign-unknown", "penalize", "ignore")
+    eng.set_taxonomy(tax5)
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+        parity = {}
+        for mode in modes:
+            P = OrgscorerParams(n_systems=1, weak_loci=mode)
+            eng.set_params(P)
+            ref = c_oracle.score_batch(P, tax5, chunk, threads=os.cpu_count() or 1)
+            parity[mode] = parity_report(ref, eng.score_batch(chunk), chunk.n_contigs, SCORE_RTOL,
+                                         "oracle/orgscorer_oracle.c")["bit_exact"]
+    P = OrgscorerParams(n_systems=1, weak_loci=modes[0])
+    eng.set_params(P)
+    pin = PinnedArena()
+    packed = chunk.can_pack(len(tax5.tables()["parent"]), 1)
+    wire = chunk.to_packed(P.min_scov) if packed else chunk.arrays()
+    harr = {k: pin.like(np.ascontiguousarray(v)) for k, v in wire.items()}
+    h2d = int(sum(v.nbytes for v in harr.values()))
+    host_buf, counts, d2h = None, np.zeros(3, np.int64), 0
+
+    def one_chunk():
+        nonlocal host_buf, d2h
+        eng.score_batch_device(harr)
+        blob, stream = wdist.device_blob(eng)
+        with torch.cuda.stream(stream):
+            if host_buf is None or host_buf.numel() < blob.numel():
+                host_buf = torch.empty(blob.numel(), dtype=torch.uint8, pin_memory=True)
+            host_buf[:blob.numel()].copy_(blob, non_blocking=True)
+            stream.synchronize()
+        d2h = int(blob.numel())
+        return blob.numel()
+
+    nb = one_chunk()   # warm-up (allocations)
+    from waafle_b200.engine import unpack_results
+    one = unpack_results(host_buf.numpy()[:nb])["call_counts"]
+    barrier()
+    t = time.perf_counter()
+    kms = 0.0
+    for _ in range(mine):
+        one_chunk()
+        counts += one
+        kms += eng.stats()["ms_kernels"]
+    barrier()
+    ms = 1e3 * (time.perf_counter() - t)
+    tv = torch.tensor([ms, kms], dtype=torch.float64, device="cuda")
+    cv = torch.tensor(counts.tolist() + [mine], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cv, op=dist.ReduceOp.SUM)
+    ms, kms = tv.tolist()
+    tot = cv.tolist()
+    host_buf = None
+    torch.cuda.synchronize()
+    pin.close()
+    n_total = tot[3] * chunk.n_contigs
+    return {"workload": workload_name("cfg5", n_total) + ": {} chunks of {} contigs, chunk k on rank k % {}".format(
+                tot[3], chunk.n_contigs, world),
+            "flags": "--weak-loci assign-unknown, annotation transfer (1 system)", "contigs_total": n_total,
+            "hits_total": int(chunk.n_hits) * tot[3], "value": n_total / (ms * 1e-3), "unit": UNIT,
+            "seconds": ms * 1e-3, "kernels_ms_max_rank": kms,
+            "what": "per chunk: pinned host buffers -> plugin call -> packed result records D2H; counts all-reduced at the end",
+            "h2d_bytes_per_chunk": h2d, "d2h_bytes_per_chunk": d2h,
+            "wire_format": "packed 15 B/hit" if packed else "wide 33 B/hit",
+            "calls": {"lgt": tot[0], "no_lgt": tot[1], "unclassified": tot[2]},
+            "parity_one_chunk_vs_c_oracle": parity}
 
 
 if __name__ == "__main__":

@@ -236,6 +236,17 @@ int  wfl_parse_fetch(wfl_parser *p, const int32_t *sys_perm, int32_t *qstart, in
                      int64_t *q_off, int32_t *q_len);
 int  wfl_parser_times(const wfl_parser *p, float *ms_h2d, float *ms_kernels, float *ms_d2h);
 
+/* ---- waafle_genecaller on the device: gene calls from BLAST hits ------------------------------------
+ * Replaces the per-contig body of waafle/waafle_genecaller.py:207-230 (hits2ints :107-113, overlap_intervals :137-168,
+ * merge_inodes :121-135 over INode / calc_overlap, waafle/utils.py:455-500).  Contig blocks are consecutive runs of one
+ * query in the blastout (iter_contig_hits, utils.py:255-270): hits [block_off[b], block_off[b+1]).  keep[h] = the hit passed
+ * --min-scov.  The genes of block b come back at [block_off[b], block_off[b] + gene_count[b]) of the gene arrays (each as
+ * long as the hit arrays), in the reference's output order.  `--stranded` has no effect upstream (:215 compares a bool with
+ * "on") and is therefore not a parameter.  Host pointers in and out; returns a wfl_status. */
+int  wfl_call_genes(int device, int64_t n_blocks, const int64_t *block_off, const int32_t *qstart, const int32_t *qend,
+                    const int8_t *strand, const uint8_t *keep, double min_overlap, double min_gene_length,
+                    int32_t *gene_start, int32_t *gene_end, int8_t *gene_strand, int32_t *gene_count, float *ms_kernel);
+
 /* Page-locked host memory for callers without a CUDA binding of their own (pinned buffers make the
  * H2D / D2H copies of wfl_score_batch asynchronous and ~2x faster).  Free with wfl_host_free. */
 int  wfl_host_alloc(size_t bytes, void **out);

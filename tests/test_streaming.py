@@ -107,7 +107,7 @@ def test_synthetic_annotated_streamed_equals_single_pass(tmp_path):
     with open(files["blastout"], "w") as fh:
         fh.write("\n".join(rows))
     with open(files["contigs"], "a") as fh:
-        fh.write(">zz_nohits_1 x\nACGT\n>aa_nohits_2\nACGTACGT\n")
+        fh.write(">zz_nohits_1 x\nACGT\n>aa_nohits_2\nACGTACGT\n")   # no hits, no loci: every cell prints "--"
     flags = dict(weak_loci="assign-unknown")
     one, two = tmp_path / "one", tmp_path / "two"
     one.mkdir()

@@ -263,17 +263,32 @@ __device__ __forceinline__ bool near_print_edge(double v) {
     const double x = v * 1e4;
     return fabs(x - floor(x) - 0.5) <= 1e-7;
 }
-// rows_exact: exact gene scores of clade t, lane per locus.  Records of a
+// Loci whose gene scores decide the reported scores of clade t1 (or of the pair t1, t2): all non-ignored loci if the rank is
+// near a print edge, else only those attaining the minimum (crit).
+__device__ __forceinline__ u32 edge_loci(const FLevel &L, int t1, int t2, double crit, double rank, int lane) {
+    if (near_print_edge(rank)) return L.um;
+    bool sel = false;
+    if ((L.um >> lane) & 1u) {
+        RowRef w1, w2;
+        w1.open(L, t1);
+        w2.open(L, t2 >= 0 ? t2 : t1);
+        const double v = fmax(w1.at(L, lane), w2.at(L, lane));
+        sel = v <= crit + 1e-11;
+    }
+    return __ballot_sync(FULL, sel);
+}
+
+// rows_exact: exact gene scores of clade t at the loci `loci`, lane per locus.  Records of a
 // locus are sorted by (clade, score descending): the group is found by binary search.  Groups of more than LC records go
 // through the warp's global scratch, one at a time.
 constexpr int LC = 24;
-__device__ __noinline__ void rows_exact(const FastArgs &a, char *cold, int coldcap, const FLevel &L, double *row, int t, int lane, int G,
-                                        const u16 *l_base, const int *l_lo, const u16 *rec, const u32 *hsp, const int *hcl,
-                                        const double *hv) {
+__device__ __noinline__ void rows_exact(const FastArgs &a, char *cold, int coldcap, const FLevel &L, double *row, int t, u32 loci,
+                                        int lane, const u16 *l_base, const int *l_lo, const u16 *rec, const u32 *hsp,
+                                        const int *hcl, const double *hv) {
     if (t == L.t_unk) return;   // (dense row: the caller does not report it from here)
     const u32 pm = L.pres[t];
     const int clade = L.cl_id[t];
-    const bool act = lane < G && ((pm >> lane) & 1u);
+    const bool act = ((pm & loci) >> lane) & 1u;
     bool big = false;
     int r0 = 0, lend = 0, lmin = 0, n = 1;
     double sc = 0.0;
@@ -966,7 +981,8 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         // a reported score the writer would round the other way if it were 1e-12 off: recompute the clade's
                         // gene scores in numpy's summation order (the dense Unknown row: exact pipeline)
                         if (tb == t_unk) { trip = true; break; }
-                        rows_exact(a, cold, F.Hcap, L, row, tb, lane, G, l_base, l_lo, rec, hsp, hcl, hv);
+                        const u32 el = edge_loci(L, tb, -1, R.crit, R.rank, lane);
+                        rows_exact(a, cold, F.Hcap, L, row, tb, el, lane, l_base, l_lo, rec, hsp, hcl, hv);
                         R.rank = row_stats(L, tb, -1, &R.crit);
                         if (lane == 0) ++stat[ST_REFINED];
                     }
@@ -1156,8 +1172,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         R.rank = brank;
                         if (near_print_edge(bcrit) || near_print_edge(brank)) {   // see the one-clade search
                             if (be.t1 == t_unk || be.t2 == t_unk) { trip = true; break; }
-                            rows_exact(a, cold, F.Hcap, L, row, be.t1, lane, G, l_base, l_lo, rec, hsp, hcl, hv);
-                            rows_exact(a, cold, F.Hcap, L, row, be.t2, lane, G, l_base, l_lo, rec, hsp, hcl, hv);
+                            const u32 el = edge_loci(L, be.t1, be.t2, bcrit, brank, lane);
+                            rows_exact(a, cold, F.Hcap, L, row, be.t1, el, lane, l_base, l_lo, rec, hsp, hcl, hv);
+                            rows_exact(a, cold, F.Hcap, L, row, be.t2, el, lane, l_base, l_lo, rec, hsp, hcl, hv);
                             R.rank = row_stats(L, be.t1, be.t2, &R.crit);
                             if (lane == 0) ++stat[ST_REFINED];
                         }

@@ -188,7 +188,7 @@ def write_shard(records, prefix):
     for r in sorted(records, key=lambda r: r["contig_name"]):
         opt = r["call"]
         cells = [writer.format_field(r[f]) for f in writer.FORMATS[opt]]
-        ann = ["|".join(d.get(s, writer.C_MISSING_ANNOTATION) for d in r["annotations"]) for s in systems]
+        ann = [writer.format_field("|".join(d.get(s, writer.C_MISSING_ANNOTATION) for d in r["annotations"])) for s in systems]
         handles[opt].write(SHARD_SEP.join([r["contig_name"], str(len(r["annotations"]))] + cells + ann) + "\n")
     for fh in handles.values():
         fh.close()
