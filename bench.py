@@ -612,7 +612,7 @@ def stream_leg(args, eng, dist, world, rank, barrier):
     import torch
     from waafle_b200 import dist as wdist
     from waafle_b200.engine import PinnedArena
-    from waafle_b200.params import OrgscorerParams
+    from waafle_b200.params import WEAK_LOCI, OrgscorerParams
     from waafle_b200 import synth
     data = synth.generate_config("cfg5", n_contigs=args.stream_chunk, seed=1000, annotations=True)
     tax5 = data.taxonomy()
@@ -626,12 +626,12 @@ def stream_leg(args, eng, dist, world, rank, barrier):
         from oracle import c_oracle
         parity = {}
         for mode in modes:
-            P = OrgscorerParams(n_systems=1, weak_loci=mode)
+            P = OrgscorerParams(n_systems=1, weak_loci=WEAK_LOCI[mode])
             eng.set_params(P)
             ref = c_oracle.score_batch(P, tax5, chunk, threads=os.cpu_count() or 1)
             parity[mode] = parity_report(ref, eng.score_batch(chunk), chunk.n_contigs, SCORE_RTOL,
                                          "oracle/orgscorer_oracle.c")["bit_exact"]
-    P = OrgscorerParams(n_systems=1, weak_loci=modes[0])
+    P = OrgscorerParams(n_systems=1, weak_loci=WEAK_LOCI[modes[0]])
     eng.set_params(P)
     pin = PinnedArena()
     packed = chunk.can_pack(len(tax5.tables()["parent"]), 1)

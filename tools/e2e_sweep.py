@@ -29,10 +29,12 @@ def main():
     steps = int(argv[2]) if len(argv) > 2 else 8
     data = synth.generate_config(workload, n_contigs=n, seed=1000)
     tax = data.taxonomy()
-    batch = data.to_batch(tax)
+    batch = data.to_batch(tax).sort_hits()   # what the front end's packer delivers
     P = OrgscorerParams(n_systems=1 if batch.hit_sysmask is not None else 0)
     pin = PinnedArena()
-    harr = {k: pin.like(np.ascontiguousarray(v)) for k, v in batch.arrays().items()}
+    wide = os.environ.get("WFL_SWEEP_WIDE") == "1" or not batch.can_pack(len(tax.tables()["parent"]), P.n_systems)
+    wire = batch.arrays() if wide else batch.to_packed(P.min_scov)
+    harr = {k: pin.like(np.ascontiguousarray(v)) for k, v in wire.items()}
     first = None
     for g in groups:
         env = dict(kv.split("=", 1) for kv in g.split()) if g else {}

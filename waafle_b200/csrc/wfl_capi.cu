@@ -55,8 +55,9 @@ struct wfl_engine {
     size_t fast_scratch_slot = 0;        // bytes of fast-kernel scratch per compute stream
     int plan_nmax = 0;
     int tax_max_depth = 0, anc_rows = 0;
+    FastCfg fcfgp{};                    // pairs pass: first-pass capacities with a large survivor-pair list
     FastCfg fcfg{}, fcfg2{};            // first pass (all contigs) / second pass (capacity overflows, larger slice)
-    int fast_grid = 0, fast_grid2 = 0;
+    int fast_grid = 0, fast_grid2 = 0, fast_gridp = 0;
     int64_t cfg_key[4] = {-1, -1, -1, -1};
     // exact pipeline state
     Buf pipe_pool[2], pipe_ctg, pipe_lists[2], pipe_cnt[2], pipe_wq[2], k2_desc[2], k2_order[2], k2_keys[2], k2_meta[2];
@@ -542,9 +543,11 @@ void choose_fast_cfg(wfl_engine *e) {
     const int T = e->fast_tcap ? e->fast_tcap : std::min(4096, std::max(64, r16(0.42 * H + 16)));
     const int N = e->fast_ncap ? e->fast_ncap : std::min(16384, std::max(96, r16(0.6 * H + 32)));
     fit_layout(e, e->fcfg, H, M, T, N, 64);
+    fit_layout(e, e->fcfgp, H, M, T, N, 1024);          // same slice, room for many two-clade survivor pairs
     fit_layout(e, e->fcfg2, 3 * H, 3 * M, 3 * T, 3 * N, 2048);
     e->fast_grid = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfg, e->packed, 0));
     e->fast_grid2 = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfg2, e->packed, 0));
+    e->fast_gridp = e->sm_count * std::max(1, fast_ctas_per_sm(e->fcfgp, e->packed, 0));
     memcpy(e->cfg_key, key, sizeof key);
 }
 
@@ -554,15 +557,24 @@ int launch_fast_pass(wfl_engine *e, DevCounters *ctr, int pass, int64_t c0, int6
     cudaStream_t stream = slot ? e->stream2 : e->stream;
     FastArgs a{};
     a.b = e->b; a.t = e->tax; a.o = e->o; a.P = e->P; a.ctr = ctr;
-    a.cfg = pass ? e->fcfg2 : e->fcfg;
+    // pass 0: every contig; pass 1 ("pairs"): first-pass contigs whose survivor-pair list overflowed, same slice with a large
+    // Scap; pass 2: every other capacity overflow of passes 0 / 1, slice ~3x as large; what that cannot hold: exact pipeline
+    a.cfg = pass == 0 ? e->fcfg : pass == 1 ? e->fcfgp : e->fcfg2;
     a.wq = static_cast<unsigned long long *>(e->fast_wq.p) + launch_idx;
-    int *fb_a = static_cast<int *>(e->fb_list.p), *fb_b = fb_a + e->n + 1;
+    int *fb_a = static_cast<int *>(e->fb_list.p), *fb_b = fb_a + e->n + 1, *fb_p = fb_b + e->n + 1;
     a.fb_final = fb_b;
     a.fb_final_count = &ctr->n_fallback2;
+    const bool multi = e->fast_passes > 1;
     if (pass == 0) {
         a.n_work = n_work; a.work_base = c0; a.work_list = nullptr; a.n_work_dev = nullptr;
-        a.fb_list = e->fast_passes > 1 ? fb_a : fb_b;
-        a.fb_count = e->fast_passes > 1 ? &ctr->n_fallback : &ctr->n_fallback2;
+        a.fb_list = multi ? fb_a : fb_b;
+        a.fb_count = multi ? &ctr->n_fallback : &ctr->n_fallback2;
+        a.fb_pairs = multi ? fb_p : nullptr;
+        a.fb_pairs_count = &ctr->n_fallback_pairs;
+    } else if (pass == 1) {
+        a.n_work = 0; a.work_base = 0; a.work_list = fb_p; a.n_work_dev = &ctr->n_fallback_pairs;
+        a.fb_list = fb_a;
+        a.fb_count = &ctr->n_fallback;
     } else {
         a.n_work = 0; a.work_base = 0; a.work_list = fb_a; a.n_work_dev = &ctr->n_fallback;
         a.fb_list = fb_b;
@@ -581,7 +593,7 @@ int launch_fast_pass(wfl_engine *e, DevCounters *ctr, int pass, int64_t c0, int6
     a.plan_data = static_cast<const uint16_t *>(e->plan_data.p);
     a.scratch = static_cast<char *>(e->fast_scratch.p) + (size_t)slot * e->fast_scratch_slot;   // launches on the two streams overlap
     const int wpc = fast_warps_per_cta();
-    const int grid = pass ? e->fast_grid2 : (int)std::max<int64_t>(1, std::min<int64_t>(e->fast_grid, (n_work + wpc - 1) / wpc));
+    const int grid = pass == 2 ? e->fast_grid2 : pass == 1 ? e->fast_gridp : (int)std::max<int64_t>(1, std::min<int64_t>(e->fast_grid, (n_work + wpc - 1) / wpc));
     cudaError_t err = launch_fast(a, e->packed, grid, stream);
     if (err != cudaSuccess) { set_err(e, "fast kernel launch failed: %s", cudaGetErrorString(err)); return WFL_ERR_CUDA; }
     e->stats.kernel_launches++;
@@ -652,9 +664,9 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
     if (use_fast) {
         choose_fast_cfg(e);
         char *fs;
-        if ((rc = outbuf(e, e->fb_list, 2 * ((size_t)e->n + 1), &fb_list))) return rc;
+        if ((rc = outbuf(e, e->fb_list, 3 * ((size_t)e->n + 1), &fb_list))) return rc;
         if ((rc = outbuf(e, e->fast_wq, 256, &fwq))) return rc;
-        e->fast_scratch_slot = (std::max((size_t)e->fast_grid * e->fcfg.scratch_bytes, (size_t)e->fast_grid2 * e->fcfg2.scratch_bytes) * fast_warps_per_cta() + 255) & ~(size_t)255;
+        e->fast_scratch_slot = (std::max(std::max((size_t)e->fast_grid * e->fcfg.scratch_bytes, (size_t)e->fast_gridp * e->fcfgp.scratch_bytes), (size_t)e->fast_grid2 * e->fcfg2.scratch_bytes) * fast_warps_per_cta() + 255) & ~(size_t)255;
         if ((rc = outbuf(e, e->fast_scratch, 2 * e->fast_scratch_slot, &fs))) return rc;
         CU(cudaMemsetAsync(fwq, 0, 256 * sizeof(unsigned long long), e->stream));
     }
@@ -690,7 +702,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         }
         // second pass: the contigs that overflowed a capacity of the first pass's slice, with a larger slice (their list
         // and count are on the device: no host round trip)
-        if (use_fast && e->fast_passes > 1 && (rc = launch_fast_pass(e, ctr, 1, 0, 0, 255, 0))) return rc;
+        if (use_fast && e->fast_passes > 1 && ((rc = launch_fast_pass(e, ctr, 1, 0, 0, 254, 0)) || (rc = launch_fast_pass(e, ctr, 2, 0, 0, 255, 0)))) return rc;
     }
     CU(cudaEventRecord(e->ev[2], e->stream));
     trace("kernels launched");
@@ -747,7 +759,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         // contigs for the exact pipeline: fast-path fallbacks (first round) and workspace overflows (status 1)
         std::vector<int> list;
         if (attempt == 0 && use_fast) {
-            e->stats.second_pass_contigs = e->fast_passes > 1 ? (int64_t)hc.n_fallback : 0;
+            e->stats.second_pass_contigs = e->fast_passes > 1 ? (int64_t)(hc.n_fallback + hc.n_fallback_pairs) : 0;
             for (int q = 0; q < 8; ++q) e->stats.fallback_reasons[q] = (int64_t)hc.fb_reason[q];
         }
         if (attempt == 0 && hc.n_fallback2) {

@@ -58,7 +58,8 @@ struct DevCounters {
     unsigned long long n_badinput;      // contigs with a taxon index outside the taxonomy
     unsigned long long matched_pairs, groups, levels, pairs_tested, pairs_scored, smem_contigs;
     unsigned long long n_fallback;      // contigs the first fast-path pass handed on (to the second pass)
-    unsigned long long n_fallback2;     // contigs the second pass (larger slice) handed to the exact pipeline
+    unsigned long long n_fallback_pairs;   // contigs of the first pass whose two-clade survivor list overflowed (pairs pass)
+    unsigned long long n_fallback2;     // contigs the last pass (larger slice) handed to the exact pipeline
     unsigned long long fb_reason[8];    // why (both passes): loci, hits, coordinates, records, clades, groups, pairs, guard
     unsigned long long guard_trips;     // ... of which because a rank comparison fell inside the guard band
     unsigned long long refined_groups;  // gene scores recomputed exactly inside the fast kernel (near a threshold)
@@ -113,6 +114,8 @@ struct FastArgs {
     const unsigned long long *n_work_dev;   // (second pass: the first pass's fallback count)
     int *fb_list;                  // contigs that overflowed a capacity of this pass's slice (next pass) ...
     unsigned long long *fb_count;  // ... and their number
+    int *fb_pairs;                 // contigs whose ONLY problem is the survivor-pair capacity (same slice, larger Scap) ...
+    unsigned long long *fb_pairs_count;   // ... null: they go to fb_list like the other overflows
     int *fb_final;                 // contigs for the exact pipeline (guard band, > 32 loci, long genes, ...)
     unsigned long long *fb_final_count;
     const int *anc;                // [anc_rows][n_nodes]: l-th ancestor of every node (row 0 = identity)

@@ -1239,8 +1239,12 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
             if (lane == 0) {
                 // capacity overflows are worth a second pass with a larger slice; the rest goes straight to the exact pipeline
                 const bool retry = (reason == 1 && H <= 65535) || reason == 3 || reason == 4 || reason == 5 || reason == 6;
-                const unsigned long long s = atomicAdd(retry ? a.fb_count : a.fb_final_count, 1ull);
-                (retry ? a.fb_list : a.fb_final)[s] = (int)c;
+                if (retry && reason == 6 && a.fb_pairs) {
+                    a.fb_pairs[atomicAdd(a.fb_pairs_count, 1ull)] = (int)c;
+                } else {
+                    const unsigned long long s = atomicAdd(retry ? a.fb_count : a.fb_final_count, 1ull);
+                    (retry ? a.fb_list : a.fb_final)[s] = (int)c;
+                }
                 atomicAdd(&a.ctr->fb_reason[reason & 7], 1ull);
                 // placeholder record (the speculative compaction walks every contig): overwritten by the exact pipeline
                 a.o.call[c] = WFL_CALL_UNCLASSIFIED;
