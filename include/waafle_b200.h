@@ -236,6 +236,16 @@ int  wfl_parse_fetch(wfl_parser *p, const int32_t *sys_perm, int32_t *qstart, in
                      int64_t *q_off, int32_t *q_len);
 int  wfl_parser_times(const wfl_parser *p, float *ms_h2d, float *ms_kernels, float *ms_d2h);
 
+/* ---- --write-details (waafle_orgscorer.py:766-812) -----------------------------------------------------------------
+ * With the option "details" = <capacity> set (wfl_set_option) every run goes through the exact pipeline and records, per
+ * contig and evaluated taxonomy level, every gene score of every clade (write_details :802-812 walks contig.gene_scores):
+ * entry = (contig index, evaluation index 0,1,2,..., clade node index, locus index within the contig (GFF order), score).
+ * Scores absent from the dump are 0 (a clade has no hit on that locus, :404-405).  wfl_download_details copies up to
+ * `capacity` entries (any order; a replayed contig may appear twice with identical values) and returns the number the run
+ * produced. */
+int64_t wfl_download_details(wfl_engine *e, int32_t *contig, int32_t *iteration, int32_t *clade, int32_t *locus, double *score,
+                             int64_t capacity);
+
 /* ---- waafle_genecaller on the device: gene calls from BLAST hits ------------------------------------
  * Replaces the per-contig body of waafle/waafle_genecaller.py:207-230 (hits2ints :107-113, overlap_intervals :137-168,
  * merge_inodes :121-135 over INode / calc_overlap, waafle/utils.py:455-500).  Contig blocks are consecutive runs of one

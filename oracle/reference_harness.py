@@ -69,9 +69,11 @@ def make_args(**over):
     return argparse.Namespace(**d)
 
 
-def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True, timers=None):
+def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True, timers=None, details=None):
     """Replay OS:900-960; returns {contig_name: record} in FASTA order.  `timers` (dict) receives the seconds spent
-    inside the engine region OS:952-960 ("engine") and in the whole replay including the parsers ("total")."""
+    inside the engine region OS:952-960 ("engine") and in the whole replay including the parsers ("total").
+    `details`: a TEXT file object that receives what --write-details writes (OS:931-937, 802-812; upstream opens its
+    gzip in binary mode and dies on Python 3 -- the rows themselves are produced by the unmodified write_details)."""
     wu, wo = _import()
     t_total = time.perf_counter()
     t_engine = 0.0
@@ -99,6 +101,8 @@ def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True, timers
         if name in cs:
             cs[name].attach_loci(loci)
     level0 = {}
+    if details is not None:
+        wu.write_rowdict(None, wo.c_formats["details"], file=details)
     for name, hits in wu.iter_contig_hits(blastout):
         if name not in cs:
             continue
@@ -112,7 +116,7 @@ def run_reference(contigs, blastout, gff, taxonomy, args, canonical=True, timers
             for _ in range(args.jump_taxonomy):
                 C.raise_taxonomy(tax)
         if not all([L.ignore for L in C.loci]):
-            wo.evaluate_contig(C, tax, None, args)
+            wo.evaluate_contig(C, tax, details, args)
         t_engine += time.perf_counter() - t0
     if timers is not None:
         timers["engine"] = t_engine

@@ -28,6 +28,10 @@ CLI_FLAG_SETS = [
 ]
 
 
+DETAILS_FLAG_SETS = [{}, dict(weak_loci="assign-unknown"), dict(jump_taxonomy=1, weak_loci="penalize")]
+DETAILS_CLI = [[], ["--weak-loci", "assign-unknown"], ["--jump-taxonomy", "1", "--weak-loci", "penalize"]]
+
+
 def main():
     out_root = os.path.join(HERE, "demo_cli")
     shutil.rmtree(out_root, ignore_errors=True)
@@ -52,6 +56,21 @@ def main():
             for kind, text in texts[0].items():
                 with open(os.path.join(dst, "demo_contigs.{}.tsv".format(kind)), "w") as fh:
                     fh.write(text)
+    # --write-details: the unmodified write_details through the harness (text handle; canonical clade order)
+    import gzip
+    import io
+    sys.path.insert(0, ROOT)
+    from oracle import reference_harness as rh
+    for gff in ("genecaller", "prodigal"):
+        files = helpers.demo_files(tmp, gff == "prodigal")
+        for k, over in enumerate(DETAILS_FLAG_SETS):
+            buf = io.StringIO()
+            rh.run_reference(files["contigs"], files["blastout"], files["gff"], files["taxonomy"], rh.make_args(**over),
+                             details=buf)
+            with gzip.open(os.path.join(out_root, "details_{}_{}.tsv.gz".format(gff, k)), "wt") as fh:
+                fh.write(buf.getvalue())
+    with open(os.path.join(out_root, "details_flag_sets.json"), "w") as fh:
+        json.dump(DETAILS_FLAG_SETS, fh)
     with open(os.path.join(out_root, "flag_sets.json"), "w") as fh:
         json.dump(CLI_FLAG_SETS, fh)
     print("wrote", out_root)

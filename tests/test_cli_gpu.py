@@ -85,3 +85,28 @@ def test_streamed_two_workers_equal_single_call_on_synthetic(tmp_path):
         two = run_cli(files, tmp_path / ("two_" + mode), ["--weak-loci", mode, "--stream-mb", "2", "--devices", "0,0"])
         assert one == two, mode
         assert one["no_lgt"].count("\n") > 100
+
+
+@pytest.mark.parametrize("gff", ["genecaller", "prodigal"])
+def test_write_details_equals_reference_write_details(tmp_path, gff):
+    """--write-details (OS:766-812): <basename>.details.tsv.gz == what the unmodified write_details prints through the
+    reference harness (tests/golden/demo_cli/details_*.tsv.gz; canonical clade order), default flags, a spiked Unknown
+    and --jump-taxonomy."""
+    import gzip
+    import json
+    root = os.path.join(helpers.GOLDEN, "demo_cli")
+    flag_sets = json.load(open(os.path.join(root, "details_flag_sets.json")))
+    cli = [[], ["--weak-loci", "assign-unknown"], ["--jump-taxonomy", "1", "--weak-loci", "penalize"]]
+    assert len(cli) == len(flag_sets)
+    files = helpers.demo_files(tmp_path, gff == "prodigal")
+    for k, extra in enumerate(cli):
+        outdir = tmp_path / "d{}".format(k)
+        run_cli(files, outdir, extra + ["--write-details"])
+        with gzip.open(os.path.join(str(outdir), "demo_contigs.details.tsv.gz"), "rt") as fh:
+            got = fh.read()
+        with gzip.open(os.path.join(root, "details_{}_{}.tsv.gz".format(gff, k)), "rt") as fh:
+            want = fh.read()
+        if got != want:
+            g, w = got.split("\n"), want.split("\n")
+            bad = next((i for i in range(min(len(g), len(w))) if g[i] != w[i]), min(len(g), len(w)) - 1)
+            raise AssertionError((gff, extra, len(g), len(w), g[bad][:300], w[bad][:300]))

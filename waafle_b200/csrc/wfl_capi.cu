@@ -52,6 +52,8 @@ struct wfl_engine {
     // device buffers (grow-only)
     Buf tx[4], anc, in[12], out[18], ctr, work, scratch, cm[5], dbg[4], plan_index, plan_data;
     Buf fb_list, fast_scratch, fast_wq, blob, status_tmp;
+    Buf det[6];                          // --write-details dump: contig, iteration, clade, locus, score, count
+    int64_t det_cap = 0, det_used = 0;
     size_t fast_scratch_slot = 0;        // bytes of fast-kernel scratch per compute stream
     int plan_nmax = 0;
     int tax_max_depth = 0, anc_rows = 0;
@@ -443,6 +445,15 @@ int launch_pipeline(wfl_engine *e, DevCounters *ctr, const int *list, int64_t c0
         pa.k2_cap = cap;
         CU(cudaMemsetAsync(k2meta, 0, 66 * sizeof(K2Meta), stream));
     }
+    if (e->det_cap > 0) {
+        pa.det_count = static_cast<unsigned long long *>(e->det[5].p);
+        pa.det_cap = e->det_cap;
+        pa.det_contig = static_cast<int32_t *>(e->det[0].p);
+        pa.det_iter = static_cast<int32_t *>(e->det[1].p);
+        pa.det_clade = static_cast<int32_t *>(e->det[2].p);
+        pa.det_locus = static_cast<int32_t *>(e->det[3].p);
+        pa.det_score = static_cast<double *>(e->det[4].p);
+    }
     pa.dbg_contig = dbg_contig;
     if (dbg_contig >= 0) {
         pa.dbg_clade = static_cast<int32_t *>(e->dbg[0].p);
@@ -658,7 +669,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
     if ((rc = outbuf(e, e->cm[4], (size_t)e->o.mem_pool_cap, &cm_members))) return rc;
     cm_totals = cm_counts + 4;
     if ((rc = outbuf(e, e->scratch, compaction_scratch_elems(e->n), &scan_tmp))) return rc;
-    const bool use_fast = !e->exact && e->P.p.min_overlap > 0.0;
+    const bool use_fast = !e->exact && e->det_cap == 0 && e->P.p.min_overlap > 0.0;
     int *fb_list = nullptr;
     unsigned long long *fwq = nullptr;
     if (use_fast) {
@@ -671,6 +682,15 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
         CU(cudaMemsetAsync(fwq, 0, 256 * sizeof(unsigned long long), e->stream));
     }
     CU(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), e->stream));
+    if (e->det_cap > 0) {   // --write-details dump (exact pipeline only)
+        int32_t *p4;
+        double *p8;
+        unsigned long long *pc;
+        for (int q = 0; q < 4; ++q)
+            if ((rc = outbuf(e, e->det[q], (size_t)e->det_cap, &p4))) return rc;
+        if ((rc = outbuf(e, e->det[4], (size_t)e->det_cap, &p8)) || (rc = outbuf(e, e->det[5], 1, &pc))) return rc;
+        CU(cudaMemsetAsync(pc, 0, sizeof(unsigned long long), e->stream));
+    }
     CU(cudaEventRecord(e->ev[1], e->stream));
 
     if (e->n > 0) {
@@ -1005,6 +1025,7 @@ int wfl_set_option(wfl_engine *e, const char *name, int64_t value) {
     else if (k == "fast_hscale_pct") e->fast_hscale = std::max<int64_t>(50, value) / 100.0;
     else if (k == "fast_mcap") e->fast_mcap = (int)std::max<int64_t>(0, value);
     else if (k == "fast_tcap") e->fast_tcap = (int)std::max<int64_t>(0, value);
+    else if (k == "details") e->det_cap = std::max<int64_t>(0, value);
     else if (k == "fast_passes") e->fast_passes = value >= 2 ? 2 : 1;
     else if (k == "fast_ncap") e->fast_ncap = (int)std::max<int64_t>(0, value);
     else if (k == "pool_mb") e->pipe_pool_bytes = (size_t)std::max<int64_t>(0, value) << 20;
@@ -1064,6 +1085,7 @@ void wfl_destroy(wfl_engine *e) {
     for (auto &b : e->cm) fr(b);
     for (auto &b : e->dbg) fr(b);
     fr(e->anc); fr(e->ctr); fr(e->work); fr(e->scratch); fr(e->plan_index); fr(e->plan_data);
+    for (auto &b : e->det) fr(b);
     fr(e->fb_list); fr(e->fast_scratch); fr(e->fast_wq); fr(e->blob); fr(e->status_tmp);
     for (int q = 0; q < 2; ++q) { fr(e->pipe_pool[q]); fr(e->pipe_lists[q]); fr(e->pipe_cnt[q]); fr(e->pipe_wq[q]); }
     fr(e->pipe_ctg);
@@ -1222,6 +1244,24 @@ int wfl_pack_results(wfl_engine *e, void **dev_ptr, int64_t *bytes, void **strea
     *bytes = total;
     if (stream) *stream = e->stream;
     return WFL_OK;
+}
+
+int64_t wfl_download_details(wfl_engine *e, int32_t *contig, int32_t *iteration, int32_t *clade, int32_t *locus, double *score,
+                             int64_t capacity) {
+    if (!e) return WFL_ERR_ARG;
+    if (!e->have_results || e->det_cap <= 0 || !e->det[5].p) { set_err(e, "no details: set option details=<capacity> and run"); return WFL_ERR_STATE; }
+    CU(cudaSetDevice(e->device));
+    unsigned long long cnt = 0;
+    CU(cudaMemcpy(&cnt, e->det[5].p, sizeof cnt, cudaMemcpyDeviceToHost));
+    const size_t m = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)std::min<int64_t>(capacity, e->det_cap));
+    if (m && contig && iteration && clade && locus && score) {
+        CU(cudaMemcpy(contig, e->det[0].p, m * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(iteration, e->det[1].p, m * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(clade, e->det[2].p, m * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(locus, e->det[3].p, m * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(score, e->det[4].p, m * 8, cudaMemcpyDeviceToHost));
+    }
+    return (int64_t)cnt;   // entries the run produced (may exceed the capacity: run again with a larger one)
 }
 
 int wfl_host_alloc(size_t bytes, void **out) {

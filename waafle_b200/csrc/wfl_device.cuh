@@ -187,6 +187,11 @@ struct PipeArgs {
     unsigned int *k2_keys;         // sort key of every descriptor (compact copy for the counting sort)
     unsigned long long k2_cap;
     K2Meta *k2_meta;               // this level's
+    // --write-details (waafle_orgscorer.py:802-812): every gene score of every clade, per contig and evaluated level
+    unsigned long long *det_count;
+    long long det_cap;
+    int32_t *det_contig, *det_iter, *det_clade, *det_locus;
+    double *det_score;
     long long dbg_contig;
     int32_t *dbg_clade, *dbg_locus;
     double *dbg_score;

@@ -924,6 +924,22 @@ __global__ void __launch_bounds__(32 * WFL_LAT_WPC, WFL_LAT_CPSM) wfl_pipe_masks
                 if (lane == 0) *a.dbg_count = Ngrp;
             }
             if (iter == 0 && nun == 0) break;   // "empty" contig, waafle_orgscorer.py:959
+            if (a.det_count) {   // write_details (:802-812): the level's gene scores, one entry per (clade, locus) group
+                unsigned long long dbase = 0;
+                if (lane == 0) dbase = atomicAdd(a.det_count, (unsigned long long)Ngrp);
+                dbase = __shfl_sync(FULL, dbase, 0);
+#pragma unroll 1
+                for (int g = lane; g < Ngrp; g += 32) {
+                    const unsigned long long o = dbase + g;
+                    if ((long long)o < a.det_cap) {
+                        a.det_contig[o] = (int32_t)c;
+                        a.det_iter[o] = iter;
+                        a.det_clade[o] = cl_id[g_t[g]];
+                        a.det_locus[o] = l_raw[g_loc[g]];
+                        a.det_score[o] = g_score[g];
+                    }
+                }
+            }
             // ---- clade rows + gene bitmasks ----------------------------------------------------
             // every rank in [0, T) owns >= 1 group (the spiked Unknown owns G)
             DECL_CLADES

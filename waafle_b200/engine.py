@@ -27,7 +27,7 @@ EXPORTS = ["wfl_abi_version", "wfl_device_count", "wfl_create", "wfl_destroy", "
            "wfl_upload_packed", "wfl_run_resident", "wfl_download_results", "wfl_get_stats", "wfl_set_option",
            "wfl_pack_results", "wfl_packed_results_layout", "wfl_debug_gene_scores", "wfl_host_alloc",
            "wfl_host_free", "wfl_parser_create", "wfl_parser_destroy", "wfl_parser_last_error", "wfl_parse_blast",
-           "wfl_parse_distinct", "wfl_parse_fetch", "wfl_parser_times", "wfl_call_genes"]
+           "wfl_parse_distinct", "wfl_parse_fetch", "wfl_parser_times", "wfl_call_genes", "wfl_download_details"]
 ABI_VERSION = 2
 _CUDA_TOUCHED = False   # this process has initialised CUDA through the library (a fork could not use it any more)
 
@@ -283,6 +283,10 @@ class Engine:
         if self._pinned is not None:
             key = (n, nl, S, max(1, members_capacity))
             if key not in self._res_cache:
+                # a new shape: the previous shape's page-locked buffers go back first (arrays handed out by earlier calls
+                # are documented to die with the next call), so a long-lived engine does not accumulate pinned memory
+                self._res_cache = {}
+                self._pinned.close()
                 e = self._pinned.empty
                 self._res_cache = {key: dict(
                     call=e(n, np.uint8), direction=e(n, np.uint8), lifts=e(n, np.int32), clade1=e(n, np.int32),
@@ -361,6 +365,34 @@ class Engine:
         p, nb, st = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_void_p()
         self._check(self._lib.wfl_pack_results(self._h, ctypes.byref(p), ctypes.byref(nb), ctypes.byref(st)))
         return p.value, nb.value, st.value
+
+    def score_batch_details(self, batch):
+        """--write-details: (results, details) where details = dict of arrays contig / iteration / clade / locus / score --
+        every gene score of every clade at every evaluated level (exact pipeline; see include/waafle_b200.h)."""
+        self.set_option("details", 0)
+        self.set_option("exact", 1)
+        self.score_batch(batch)
+        st = self.stats()
+        cap = int(st["groups"]) + int(st["levels"]) * 64 + 4096
+        lib = self._lib
+        P = ctypes.POINTER
+        lib.wfl_download_details.restype = ctypes.c_int64
+        lib.wfl_download_details.argtypes = [ctypes.c_void_p, P(ctypes.c_int32), P(ctypes.c_int32), P(ctypes.c_int32),
+                                             P(ctypes.c_int32), P(ctypes.c_double), ctypes.c_int64]
+        for _ in range(4):
+            self.set_option("details", cap)
+            res = self.score_batch(batch)
+            d = dict(contig=np.empty(cap, np.int32), iteration=np.empty(cap, np.int32), clade=np.empty(cap, np.int32),
+                     locus=np.empty(cap, np.int32), score=np.empty(cap, np.float64))
+            n = lib.wfl_download_details(self._h, _ptr(d["contig"], ctypes.c_int32), _ptr(d["iteration"], ctypes.c_int32),
+                                         _ptr(d["clade"], ctypes.c_int32), _ptr(d["locus"], ctypes.c_int32),
+                                         _ptr(d["score"], ctypes.c_double), cap)
+            self._check(min(int(n), 0))
+            if n <= cap:
+                self.set_option("details", 0)
+                return res, {k: v[:int(n)] for k, v in d.items()}
+            cap = int(n) + 4096
+        raise EngineError("details dump keeps overflowing")
 
     def stats(self):
         s = CStats()

@@ -4,7 +4,8 @@ Same positional arguments and flags as the reference CLI (waafle/waafle_orgscore
 the shared flags of waafle/waafle_genecaller.py:81-101), same stderr stage messages, same three
 output TSVs.  The only part that differs is the body of the major contig loop
 (waafle_orgscorer.py:952-960), which is one `Engine.score_batch` call on the GPU.
-`--write-details` is accepted but rejected at run time (it crashes on Python 3 upstream).
+`--write-details` writes <basename>.details.tsv.gz with the content the reference's write_details (OS:766-812) produces
+when given a text-mode handle (upstream opens the gzip in binary mode and fails on Python 3).
 """
 
 import argparse
@@ -127,8 +128,8 @@ def score_in_chunks(engine, batch, chunk):
 
 def main(argv=None):
     args = get_args(argv)
-    if args.write_details:
-        die("--write-details is not supported (it fails on Python 3 in the reference as well)")
+    if args.write_details and (args.devices is not None or args.stream_mb > 0):
+        die("--write-details needs the single-call path (no --devices / --stream-mb)")
     say("Loading taxonomy.")
     tax = taxonomy.Taxonomy(args.taxonomy)
     say("Initializing contigs.")
@@ -161,12 +162,22 @@ def main(argv=None):
     engine = Engine(args.device, params, tax)
     if args.exact_scores:
         engine.set_option("exact", 1)
-    res = score_in_chunks(engine, batch, args.chunk_contigs)
+    det = None
+    if args.write_details:
+        # OS:931-937: every clade's gene scores at every evaluated level (the exact pipeline records them)
+        res, det = engine.score_batch_details(batch)
+    else:
+        res = score_in_chunks(engine, batch, args.chunk_contigs)
     if not args.quiet:
         st = engine.stats()
         say("  scored {:,} contigs / {:,} hits on cuda:{} ({:.1f} ms in kernels)".format(
             batch.n_contigs, batch.n_hits, args.device, st["ms_kernels"]))
     engine.close()
+    if det is not None:
+        from .streaming import chunk_contigs
+        index = {nm: k for k, nm in enumerate(batch.contig_names)}
+        order = [index[nm] for nm in chunk_contigs(hits, contig_lengths) if nm in index]   # blastout order (OS:944)
+        writer.write_details_file(os.path.join(args.outdir, args.basename + ".details.tsv.gz"), batch, tax, params, res, det, order)
     records = writer.build_records(batch, loci, hits, tax, res)
     writer.write_main_output_files(records, args.outdir, args.basename)
     say("Finished successfully.")
