@@ -45,11 +45,21 @@ constexpr int FAST_WPC = 2;     // warps (= contigs in flight) per CTA
 constexpr int GMAX = 32;        // retained loci per contig: gene bitmasks are one 32-bit word
 constexpr int NONE16 = 0xffff;
 #ifndef WFL_FAST_CPSM
-#define WFL_FAST_CPSM 8         // resident CTAs per SM the kernel is compiled for (register budget: 128; shared memory
+#define WFL_FAST_CPSM 6         // resident CTAs per SM the kernel is compiled for (register budget: 168; shared memory
                                 // limits the residency before the registers do)
 #endif
 
 #define SM(T, off) (reinterpret_cast<T *>(slice + (off)))
+
+// warp reductions on the redux unit (sm_80+): max of 64-bit keys in two 32-bit steps, signed 32-bit max, integer sum
+__device__ __forceinline__ u64 rmax_u64(u64 v) {
+    const u32 hi = (u32)(v >> 32);
+    const u32 mh = __reduce_max_sync(FULL, hi);
+    const u32 ml = __reduce_max_sync(FULL, hi == mh ? (u32)v : 0u);
+    return ((u64)mh << 32) | (u64)ml;
+}
+__device__ __forceinline__ int rmax_i32(int v) { return __reduce_max_sync(FULL, v); }
+__device__ __forceinline__ int rsum_i32(int v) { return __reduce_add_sync(FULL, v); }
 
 // hit x locus test (waafle_orgscorer.py:365-367, utils.py:487-500) for OVERLAPPING intervals and min_overlap > 0.
 // The quotient is only formed when the comparison is within 2^-40 of the threshold (fl is monotone, so outside
@@ -944,9 +954,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     const u64 b = dbits(rank);
                     if (b > bbits || (b == bbits && cl_id[t] > bid)) { bbits = b; bid = cl_id[t]; btl = t; bcrit = crit; }
                 }
-                const u64 wb = warp_max_u64(bbits);
+                const u64 wb = rmax_u64(bbits);
                 // ties: last in name order == largest node index (meld_one :623-624, canonical order)
-                const long long wid2 = warp_max_ll((wb != 0 && bbits == wb) ? (long long)bid : -1);
+                const long long wid2 = wb != 0 ? (long long)rmax_i32(bbits == wb ? bid : -1) : -1;
                 if (wb != 0 && wid2 >= 0) {
                     const int owner = __ffs(__ballot_sync(FULL, bbits == wb && (long long)bid == wid2)) - 1;
                     const int tb = __shfl_sync(FULL, btl, owner);
@@ -990,7 +1000,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     R.b1 = R.c1 = cl_id[tb];
                     if (P.p.disambiguate_one == 1) {
                         R.c1 = warp_lca(tax, my);
-                        R.na = warp_sum(nk);
+                        R.na = rsum_i32(nk);
                     }
                     if (lane < G)   // set_synteny_one (:495-509)
                         a.o.synteny[l0 + l_raw[lane]] = ign ? '~' : ((mk0[tb] >> lane) & 1u ? 'A' : '!');
@@ -1077,9 +1087,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                     const int x = cl_id[s_a[q]], y = cl_id[s_b[q]];
                     if (bq < 0 || b > bbits || (b == bbits && (x > bx || (x == bx && y > by)))) { bbits = b; bx = x; by = y; bq = q; }
                 }
-                const u64 wb = warp_max_u64(bq >= 0 ? bbits : 0ull);
-                const long long wx = warp_max_ll((bq >= 0 && bbits == wb) ? (long long)bx : -1);
-                const long long wy = warp_max_ll((bq >= 0 && bbits == wb && (long long)bx == wx) ? (long long)by : -1);
+                const u64 wb = rmax_u64(bq >= 0 ? bbits : 0ull);
+                const long long wx = rmax_i32((bq >= 0 && bbits == wb) ? bx : -1);
+                const long long wy = rmax_i32((bq >= 0 && bbits == wb && (long long)bx == wx) ? by : -1);
                 __syncwarp();
                 if (nsurv > 0) {
                     if (P.p.sister_penalty != 0) {   // parents of the level's listed clades, once (check_sister_penalty :717-744)
@@ -1145,9 +1155,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         }
                     }
                     if (__any_sync(FULL, near)) { trip = true; break; }
-                    nk = warp_sum(nk);
-                    nbad = warp_sum(nbad);
-                    ndiff = warp_sum(ndiff);
+                    nk = rsum_i32(nk);
+                    nbad = rsum_i32(nbad);
+                    ndiff = rsum_i32(ndiff);
                     la = warp_lca(tax, la);
                     lb = warp_lca(tax, lb);
                     __syncwarp();
