@@ -170,8 +170,9 @@ def main(argv=None):
         res = score_in_chunks(engine, batch, args.chunk_contigs)
     if not args.quiet:
         st = engine.stats()
-        say("  scored {:,} contigs / {:,} hits on cuda:{} ({:.1f} ms in kernels)".format(
-            batch.n_contigs, batch.n_hits, args.device, st["ms_kernels"]))
+        say("  scored {:,} contigs / {:,} hits on cuda:{} ({:.1f} ms in kernels; {:,} contigs on the exact pipeline, "
+            "{:,} workspace replays)".format(batch.n_contigs, batch.n_hits, args.device, st["ms_kernels"],
+                                             st["fallback_contigs"], st["workspace_retries"]))
     engine.close()
     if det is not None:
         from .streaming import chunk_contigs
