@@ -54,7 +54,8 @@ def test_million_row_synthetic_blastout(tmp_path, annotations):
     gpu = parsers.read_blast_hits(files["blastout"], device=0)
     assert gpu.block_starts is not None and len(gpu.block_starts) <= 4000
     assert_same_hits(cpu, gpu)
-    t = gpu.parse_times
+    # timing of a second parse: the first one pays the CUDA module load of the parser kernels
+    t = parsers.read_blast_hits(files["blastout"], device=0).parse_times
     rate = t["rows"] / ((t["ms_h2d"] + t["ms_kernels"] + t["ms_d2h"]) * 1e-3)
     print("GPU parse: {:.1f} M hits/s (H2D {:.1f} ms, kernels {:.1f} ms, D2H {:.1f} ms, {} rows)".format(
         rate / 1e6, t["ms_h2d"], t["ms_kernels"], t["ms_d2h"], t["rows"]))
