@@ -235,6 +235,13 @@ int  wfl_parse_fetch(wfl_parser *p, const int32_t *sys_perm, int32_t *qstart, in
                      int8_t *strand, int32_t *tcode, uint32_t *sysmask, int64_t *ss_off, int32_t *ss_len, uint8_t *newblock,
                      int64_t *q_off, int32_t *q_len);
 int  wfl_parser_times(const wfl_parser *p, float *ms_h2d, float *ms_kernels, float *ms_d2h);
+/* GFF text -> locus columns (replaces the per-row Locus objects of waafle/utils.py:298-355 / iter_contig_loci :341-355):
+ * returns the number of TEXT rows; comment ('#') and empty rows come back with skip = 1.  newblock[r] = the seqname differs
+ * from the previous locus row's; (s_off, s_len) = the seqname in the text.  *flagged rows (field count != 9, non-integer
+ * coordinates, a quoted field, a strand that is not one character) send the caller to its CPU reader. */
+int64_t wfl_parse_gff(wfl_parser *p, const char *text, int64_t n_bytes, int32_t *flagged, int64_t *first_flagged);
+int  wfl_parse_gff_fetch(wfl_parser *p, int32_t *start, int32_t *end, int8_t *strand, uint8_t *skip, uint8_t *newblock,
+                         int64_t *s_off, int32_t *s_len);
 
 /* ---- --write-details (waafle_orgscorer.py:766-812) -----------------------------------------------------------------
  * With the option "details" = <capacity> set (wfl_set_option) every run goes through the exact pipeline and records, per

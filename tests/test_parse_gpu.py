@@ -99,3 +99,32 @@ def test_cli_gpu_parse_equals_cpu_parse(tmp_path):
         with open(os.path.join(str(outs["gpu"]), "run.{}.tsv".format(kind))) as f1, \
                 open(os.path.join(str(outs["cpu"]), "run.{}.tsv".format(kind))) as f2:
             assert f1.read() == f2.read(), kind
+
+
+def test_gff_parsed_on_gpu(tmp_path):
+    """GFF rows on the device == the CPU reader's LocusTable: the demo GFFs (CRLF rows of waafle_genecaller, Prodigal rows
+    with '#' comments) and a large synthetic one; a row the device does not reproduce falls back to the CPU reader."""
+    from waafle_b200 import gpu_parse, parsers, synth
+    paths = [os.path.join(helpers.GOLDEN, "demo", "demo_contigs.gff"), os.path.join(helpers.GOLDEN, "demo", "demo_contigs.prodigal.gff")]
+    data = synth.generate_config("cfg5", n_contigs=20000, seed=3)
+    paths.append(data.write_files(str(tmp_path), "big")["gff"])
+    for path in paths:
+        cpu = parsers.read_gff_loci(path)
+        gpu = parsers.read_gff_loci(path, device=0)
+        assert hasattr(gpu, "parse_times"), "the GPU parser did not run"
+        assert len(cpu) == len(gpu) and len(cpu) > 0
+        for k in ("start", "end", "strand"):
+            assert np.array_equal(getattr(cpu, k), getattr(gpu, k)), (path, k)
+        assert np.array_equal(cpu.seqname, gpu.seqname) and np.array_equal(cpu.strand_str, gpu.strand_str)
+        assert [cpu.code(j) for j in range(0, len(cpu), 97)] == [gpu.code(j) for j in range(0, len(gpu), 97)]
+    t = gpu.parse_times
+    print("GPU GFF parse: {} rows, H2D {:.2f} ms, kernels {:.2f} ms, D2H {:.2f} ms".format(t["rows"], t["ms_h2d"], t["ms_kernels"], t["ms_d2h"]))
+    p = gpu_parse.BlastParser(0)
+    good = open(paths[0], "rb").read()
+    rows = good.split(b"\n")
+    f = rows[2].split(b"\t")
+    f[3] = b"."
+    assert p.parse_gff(b"\n".join(rows[:2] + [b"\t".join(f)] + rows[3:])) is None      # non-integer coordinate
+    assert p.parse_gff(b"\n".join(rows[:2] + [b"\t".join(f[:8])] + rows[3:])) is None    # 8 fields
+    assert len(p.parse_gff(good)) == len([r for r in rows if r.strip()])
+    p.close()

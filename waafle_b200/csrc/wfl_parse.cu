@@ -324,6 +324,89 @@ __global__ void wfl_parse_sysmask(const u64 *raw, uint32_t *mask, long long n, c
     }
 }
 
+// ---- GFF rows (waafle/utils.py:298-355): seqname, start, end, strand of every locus ------------------------------
+struct GffArgs {
+    const char *text;
+    long long n_bytes;
+    const long long *row_start;   // [n_rows + 1]
+    long long n_rows;
+    int32_t *start, *end;
+    int8_t *strand;
+    uint8_t *skip;                // comment ('#') or empty row
+    uint8_t *newblock;            // seqname differs from the previous locus row's (iter_contig_loci :341-355)
+    long long *s_off;
+    int32_t *s_len;
+    int *counters;                // 2: flagged rows, 3: first flagged row
+};
+
+__device__ __forceinline__ void gff_row_span(const GffArgs &a, long long r, long long &s, long long &e) {
+    s = a.row_start[r];
+    e = a.row_start[r + 1] - 1;                       // position of the newline (or one past the text)
+    if (e > a.n_bytes) e = a.n_bytes;
+    if (e > s && a.text[e - 1] == '\r') --e;          // csv.excel_tab rows end in CRLF (the reference writes them so)
+}
+
+__global__ void __launch_bounds__(128) wfl_parse_gff_rows(const GffArgs a) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_rows) return;
+    long long s, e;
+    gff_row_span(a, r, s, e);
+    const bool skip = e <= s || a.text[s] == '#';     // :345-346 (an empty row is not a locus either)
+    a.skip[r] = skip ? 1 : 0;
+    a.newblock[r] = 0;
+    a.start[r] = a.end[r] = 0;
+    a.strand[r] = '?';
+    a.s_off[r] = s;
+    a.s_len[r] = 0;
+    if (skip) return;
+    // 9 tab-separated fields (:302-303); a field that opens with a quote is left to the CPU reader (csv quoting)
+    long long f0[9], f1[9];
+    int nf = 0;
+    long long b = s;
+    bool bad = false;
+    for (long long p = s; p <= e; ++p) {
+        if (p == e || a.text[p] == '\t') {
+            if (nf < 9) { f0[nf] = b; f1[nf] = p; }
+            ++nf;
+            if (b < e && a.text[b] == '"') bad = true;
+            b = p + 1;
+        }
+    }
+    long long v0 = 0, v1 = 0;
+    if (nf != 9) bad = true;
+    if (!bad) {
+        bad = !parse_int(a.text + f0[3], (int)(f1[3] - f0[3]), v0) || !parse_int(a.text + f0[4], (int)(f1[4] - f0[4]), v1) ||
+              v0 > 2147483647ll || v1 > 2147483647ll || f1[6] - f0[6] != 1 || f1[0] - f0[0] <= 0 || f1[0] - f0[0] > 2147483647ll;
+    }
+    if (bad) {
+        atomicAdd(&a.counters[2], 1);
+        atomicMin(&a.counters[3], (int)(r > 2147483647ll ? 2147483647ll : r));
+        return;
+    }
+    a.start[r] = (int32_t)v0;
+    a.end[r] = (int32_t)v1;
+    a.strand[r] = (int8_t)a.text[f0[6]];
+    a.s_off[r] = f0[0];
+    a.s_len[r] = (int32_t)(f1[0] - f0[0]);
+    // contig block start: the previous locus row (comments skipped) names another sequence
+    long long q = r - 1;
+    bool nb = true;
+    while (q >= 0) {
+        long long qs, qe;
+        gff_row_span(a, q, qs, qe);
+        if (qe > qs && a.text[qs] != '#') {
+            long long t = qs;
+            while (t < qe && a.text[t] != '\t') ++t;
+            const long long len = t - qs;
+            nb = len != f1[0] - f0[0];
+            for (long long i = 0; !nb && i < len; ++i) nb = a.text[qs + i] != a.text[f0[0] + i];
+            break;
+        }
+        --q;
+    }
+    a.newblock[r] = nb ? 1 : 0;
+}
+
 struct PBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -339,6 +422,8 @@ struct wfl_parser {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {};
+    PBuf gcol[7];
+    long long gff_rows = 0;
     PBuf text, tiles, rows, col[13], tax_hash, tax_off, tax_len, sys_hash, sys_off, sys_len, counters, perm;
     long long n_rows = 0, n_bytes = 0;
     float ms_h2d = 0, ms_kernels = 0, ms_d2h = 0;
@@ -396,6 +481,7 @@ void wfl_parser_destroy(wfl_parser *p) {
                    &p->sys_off, &p->sys_len, &p->counters, &p->perm};
     for (PBuf *b : all) if (b->p) cudaFree(b->p);
     for (auto &b : p->col) if (b.p) cudaFree(b.p);
+    for (auto &b : p->gcol) if (b.p) cudaFree(b.p);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -515,6 +601,88 @@ int wfl_parse_fetch(wfl_parser *p, const int32_t *sys_perm, int32_t *qstart, int
     const size_t esz[12] = {4, 4, 8, 8, 1, 4, 4, 8, 4, 1, 8, 4};
     for (int i = 0; i < 12; ++i)
         if (dst[i]) PCU(cudaMemcpyAsync(dst[i], p->col[srcc[i]].p, (size_t)n * esz[i], cudaMemcpyDeviceToHost, p->stream));
+    PCU(cudaEventRecord(p->ev[1], p->stream));
+    PCU(cudaStreamSynchronize(p->stream));
+    PCU(cudaEventElapsedTime(&p->ms_d2h, p->ev[0], p->ev[1]));
+    return WFL_OK;
+}
+
+/* GFF text (waafle_genecaller / Prodigal style) parsed on the device: replaces the per-row Locus objects of
+ * waafle/utils.py:298-355.  Returns the number of text rows (comment and empty rows included: they come back with skip = 1)
+ * or a negative wfl_status; *flagged = rows the device does not reproduce (field count, non-integer coordinates, a quoted
+ * field, a strand longer than one character): the caller must then use its CPU reader. */
+int64_t wfl_parse_gff(wfl_parser *p, const char *text, int64_t n_bytes, int32_t *flagged, int64_t *first_flagged) {
+    if (!p || (!text && n_bytes) || n_bytes < 0) return WFL_ERR_ARG;
+    PCU(cudaSetDevice(p->device));
+    p->gff_rows = 0;
+    if (flagged) *flagged = 0;
+    if (first_flagged) *first_flagged = -1;
+    if (n_bytes == 0) return 0;
+    int rc;
+    const long long n_tiles = (n_bytes + TILE - 1) / TILE;
+    if ((rc = pensure(p, p->text, (size_t)n_bytes + 64)) || (rc = pensure(p, p->tiles, (size_t)(n_tiles + 1) * 8)) ||
+        (rc = pensure(p, p->counters, 16)))
+        return rc;
+    PCU(cudaEventRecord(p->ev[0], p->stream));
+    PCU(cudaMemcpyAsync(p->text.p, text, (size_t)n_bytes, cudaMemcpyHostToDevice, p->stream));
+    PCU(cudaEventRecord(p->ev[1], p->stream));
+    const int init[4] = {0, 0, 0, 2147483647};
+    PCU(cudaMemcpyAsync(p->counters.p, init, sizeof init, cudaMemcpyHostToDevice, p->stream));
+    ParseArgs a{};
+    a.text = static_cast<const char *>(p->text.p);
+    a.n_bytes = n_bytes;
+    a.tile_count = static_cast<long long *>(p->tiles.p);
+    a.n_tiles = n_tiles;
+    wfl_parse_lines_count<<<(unsigned)n_tiles, TPB, 0, p->stream>>>(a);
+    wfl_parse_lines_scan<<<1, 1024, 0, p->stream>>>(a);
+    long long n_newlines = 0;
+    PCU(cudaMemcpyAsync(&n_newlines, a.tile_count + n_tiles, 8, cudaMemcpyDeviceToHost, p->stream));
+    PCU(cudaStreamSynchronize(p->stream));
+    const bool unterminated = text[n_bytes - 1] != '\n';
+    const long long n_rows = n_newlines + (unterminated ? 1 : 0);
+    p->gff_rows = n_rows;
+    if ((rc = pensure(p, p->rows, (size_t)(n_rows + 2) * 8))) return rc;
+    const size_t esz[7] = {4, 4, 1, 1, 1, 8, 4};
+    for (int i = 0; i < 7; ++i)
+        if ((rc = pensure(p, p->gcol[i], (size_t)n_rows * esz[i]))) return rc;
+    a.row_start = static_cast<long long *>(p->rows.p);
+    a.n_rows = n_rows;
+    wfl_parse_lines_scatter<<<(unsigned)n_tiles, TPB, 0, p->stream>>>(a);
+    if (unterminated) {
+        const long long endpos = n_bytes + 1;
+        PCU(cudaMemcpyAsync(a.row_start + n_rows, &endpos, 8, cudaMemcpyHostToDevice, p->stream));
+    }
+    GffArgs g{};
+    g.text = a.text; g.n_bytes = n_bytes; g.row_start = a.row_start; g.n_rows = n_rows;
+    g.start = static_cast<int32_t *>(p->gcol[0].p); g.end = static_cast<int32_t *>(p->gcol[1].p);
+    g.strand = static_cast<int8_t *>(p->gcol[2].p); g.skip = static_cast<uint8_t *>(p->gcol[3].p);
+    g.newblock = static_cast<uint8_t *>(p->gcol[4].p); g.s_off = static_cast<long long *>(p->gcol[5].p);
+    g.s_len = static_cast<int32_t *>(p->gcol[6].p); g.counters = static_cast<int *>(p->counters.p);
+    if (n_rows > 0) wfl_parse_gff_rows<<<(unsigned)((n_rows + 127) / 128), 128, 0, p->stream>>>(g);
+    PCU(cudaGetLastError());
+    PCU(cudaEventRecord(p->ev[2], p->stream));
+    int counters[4];
+    PCU(cudaMemcpyAsync(counters, p->counters.p, sizeof counters, cudaMemcpyDeviceToHost, p->stream));
+    PCU(cudaStreamSynchronize(p->stream));
+    PCU(cudaEventElapsedTime(&p->ms_h2d, p->ev[0], p->ev[1]));
+    PCU(cudaEventElapsedTime(&p->ms_kernels, p->ev[1], p->ev[2]));
+    if (flagged) *flagged = counters[2];
+    if (first_flagged) *first_flagged = counters[2] ? counters[3] : -1;
+    return n_rows;
+}
+
+/* The columns of the last wfl_parse_gff, each [n_rows] (NULL = skip). */
+int wfl_parse_gff_fetch(wfl_parser *p, int32_t *start, int32_t *end, int8_t *strand, uint8_t *skip, uint8_t *newblock,
+                        int64_t *s_off, int32_t *s_len) {
+    if (!p) return WFL_ERR_ARG;
+    PCU(cudaSetDevice(p->device));
+    const long long n = p->gff_rows;
+    if (n == 0) return WFL_OK;
+    void *dst[7] = {start, end, strand, skip, newblock, s_off, s_len};
+    const size_t esz[7] = {4, 4, 1, 1, 1, 8, 4};
+    PCU(cudaEventRecord(p->ev[0], p->stream));
+    for (int i = 0; i < 7; ++i)
+        if (dst[i]) PCU(cudaMemcpyAsync(dst[i], p->gcol[i].p, (size_t)n * esz[i], cudaMemcpyDeviceToHost, p->stream));
     PCU(cudaEventRecord(p->ev[1], p->stream));
     PCU(cudaStreamSynchronize(p->stream));
     PCU(cudaEventElapsedTime(&p->ms_d2h, p->ev[0], p->ev[1]));

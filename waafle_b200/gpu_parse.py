@@ -34,6 +34,9 @@ def _lib():
                                            ctypes.c_int32]
         lib.wfl_parse_fetch.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 13
         lib.wfl_parser_times.argtypes = [ctypes.c_void_p, P(ctypes.c_float), P(ctypes.c_float), P(ctypes.c_float)]
+        lib.wfl_parse_gff.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64, P(ctypes.c_int32), P(ctypes.c_int64)]
+        lib.wfl_parse_gff.restype = ctypes.c_int64
+        lib.wfl_parse_gff_fetch.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 7
         _ready = True
     return lib
 
@@ -132,3 +135,40 @@ class BlastParser:
             scov_modified=cols["scov"], strand=cols["strand"], sseqid_id=None, sseqid_names=names,
             sseqid_annotations=parsers._LazyAnnotations(names), systems=systems, sysmask=cols["sysmask"],
             taxon_codes=tlut[cols["tcode"]], taxon_names=taxon_names, block_starts=starts, block_names=block_names)
+
+
+    def parse_gff(self, text):
+        """`text`: bytes of a GFF file.  Returns a parsers.LocusTable (same content as parsers.read_gff_loci), or None if
+        some row needs the CPU reader (waafle/utils.py:298-355: 9 fields, integer coordinates, '#' rows skipped)."""
+        from . import parsers
+        if not isinstance(text, (bytes, bytearray)):
+            text = bytes(text)
+        if len(text.strip()) == 0:
+            return parsers.LocusTable([], [], [], [])
+        flagged, first = ctypes.c_int32(), ctypes.c_int64()
+        n = self._lib.wfl_parse_gff(self._h, text, len(text), ctypes.byref(flagged), ctypes.byref(first))
+        self._check(n)
+        if flagged.value:
+            return None
+        n = int(n)
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        cols = dict(start=np.empty(n, np.int32), end=np.empty(n, np.int32), strand=np.empty(n, np.int8),
+                    skip=np.empty(n, np.uint8), newblock=np.empty(n, np.uint8), s_off=np.empty(n, np.int64),
+                    s_len=np.empty(n, np.int32))
+        self._check(self._lib.wfl_parse_gff_fetch(self._h, *[vp(cols[k]) for k in (
+            "start", "end", "strand", "skip", "newblock", "s_off", "s_len")]))
+        t = [ctypes.c_float() for _ in range(3)]
+        self._lib.wfl_parser_times(self._h, *[ctypes.byref(x) for x in t])
+        self.times = dict(ms_h2d=t[0].value, ms_kernels=t[1].value, ms_d2h=t[2].value, rows=n, bytes=len(text))
+        keep = np.flatnonzero(cols["skip"] == 0)
+        nb = cols["newblock"][keep]
+        starts = np.flatnonzero(nb)
+        names = [text[int(o):int(o) + int(l)].decode() for o, l in zip(cols["s_off"][keep][starts], cols["s_len"][keep][starts])]
+        counts = np.diff(np.r_[starts, len(keep)])
+        lt = parsers.LocusTable.__new__(parsers.LocusTable)
+        lt.seqname = np.repeat(np.array(names, dtype=object), counts) if len(names) else np.zeros(0, dtype=object)
+        lt.start = np.ascontiguousarray(cols["start"][keep])
+        lt.end = np.ascontiguousarray(cols["end"][keep])
+        lt.strand = np.ascontiguousarray(cols["strand"][keep])
+        lt.strand_str = lt.strand.view("S1").astype(str).astype(object)
+        return lt

@@ -135,7 +135,8 @@ def main(argv=None):
     say("Initializing contigs.")
     contig_lengths = read_contig_lengths(args.contigs)
     say("Adding gene coordinates.")
-    loci = parsers.read_gff_loci(args.gff)
+    loci = parsers.read_gff_loci(args.gff, device=None if (args.cpu_parse or args.devices is not None or args.stream_mb > 0)
+                                 else args.device)   # (a streamed run forks its workers: no CUDA in the parent before that)
     if args.basename is None:
         args.basename = os.path.split(args.contigs)[1].split(".")[0]
     say("Analyzing contigs.")

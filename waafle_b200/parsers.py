@@ -333,8 +333,22 @@ class LocusTable:
         return "{}:{}:{}".format(int(self.start[j]), int(self.end[j]), self.strand_str[j])
 
 
-def read_gff_loci(path):
-    """Parse a GFF (waafle_genecaller or Prodigal style); `#` rows are skipped (UT:345-346)."""
+def read_gff_loci(path, device=None):
+    """Parse a GFF (waafle_genecaller or Prodigal style); `#` rows are skipped (UT:345-346).  With `device` (a CUDA device
+    index) the rows are parsed on the GPU (gpu_parse.BlastParser.parse_gff); files it cannot reproduce fall through to the
+    CPU reader below, which has the reference's error behaviour."""
+    if device is not None:
+        from . import gpu_parse
+        with try_open(path) as fh:
+            text = fh.buffer.read() if hasattr(fh, "buffer") else fh.read().encode()
+        parser = gpu_parse.BlastParser(device)
+        try:
+            loci = parser.parse_gff(text)
+        finally:
+            parser.close()
+        if loci is not None:
+            loci.parse_times = parser.times
+            return loci
     with try_open(path) as fh:
         lines = [ln for ln in fh.read().split("\n") if ln and ln[0] != "#"]
     for ln in lines:
