@@ -55,6 +55,7 @@ struct wfl_engine {
     Buf det[6];                          // --write-details dump: contig, iteration, clade, locus, score, count
     int64_t det_cap = 0, det_used = 0;
     size_t fast_scratch_slot = 0;        // bytes of fast-kernel scratch per compute stream
+    bool chunks_pool_bound = false;      // the current chunk plan was cut for the exact pipeline's workspace pool
     int plan_nmax = 0;
     int tax_max_depth = 0, anc_rows = 0;
     FastCfg fcfgp{};                    // pairs pass: first-pass capacities with a large survivor-pair list
@@ -339,16 +340,27 @@ void bind_device_batch(wfl_engine *e) {
 //  * plugin call (streaming): a sub-batch is also the unit that crosses PCIe on the copy stream while its
 //    predecessor is scored: a small first chunk (the kernels start early), then equal chunks, at most ~12 per call
 //    (every chunk costs a launch chain that ends on its slowest contig).
+bool uses_fast_path(const wfl_engine *e) {
+    return !e->exact && e->det_cap == 0 && e->P.p.min_overlap > 0.0 && e->nl <= 32 * e->n;
+}
+
 void plan_chunks(wfl_engine *e, const int64_t *hoff, const int64_t *loff, bool streaming, size_t hit_row) {
     e->chunks.clear();
     e->chunks.push_back(0);
     const int64_t n = e->n;
     if (n <= 0) return;
-    const bool pool_bound = e->exact || e->P.p.min_overlap <= 0.0;
+    const bool pool_bound = !uses_fast_path(e);   // the exact pipeline's sub-batches must fit its workspace pool
+    e->chunks_pool_bound = pool_bound;
     std::vector<size_t> target;
     if (streaming) {
         const size_t total = (size_t)hoff[n] * hit_row;
-        const size_t full = e->chunk_fixed ? e->chunk_bytes : std::max(e->chunk_bytes, total / 12 + 1);
+        // fast path: one launch per chunk, ~12 chunks hide the kernels under the transfer; exact pipeline (long contigs,
+        // --exact-scores): every chunk costs a 9-launches-per-level chain that needs thousands of contigs to fill the GPU
+        // (measured at BASELINE configs[3]: 4 000 contigs in 12 chunks 136 ms per call, in one chunk 43 ms)
+        const size_t per_contig = total / (size_t)n + 1;
+        const size_t full = e->chunk_fixed ? e->chunk_bytes
+                                           : std::max(e->chunk_bytes, pool_bound ? std::max(total / 3 + 1, 8192 * per_contig)
+                                                                                 : total / 12 + 1);
         const size_t first = std::min(full / 4, e->chunk_bytes);
         size_t rem = total;
         target.push_back(std::min(rem, first));
@@ -669,7 +681,9 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
     if ((rc = outbuf(e, e->cm[4], (size_t)e->o.mem_pool_cap, &cm_members))) return rc;
     cm_totals = cm_counts + 4;
     if ((rc = outbuf(e, e->scratch, compaction_scratch_elems(e->n), &scan_tmp))) return rc;
-    const bool use_fast = !e->exact && e->det_cap == 0 && e->P.p.min_overlap > 0.0;
+    // the fused fast path holds contigs with <= 32 retained loci; a batch of long contigs (BASELINE configs[3]: 100+ genes)
+    // goes straight to the exact pipeline instead of bouncing every contig off the fast kernel first
+    const bool use_fast = uses_fast_path(e);
     int *fb_list = nullptr;
     unsigned long long *fwq = nullptr;
     if (use_fast) {
@@ -694,7 +708,7 @@ int run_once(wfl_engine *e, bool streamed, wfl_results *out, bool *restart) {
     CU(cudaEventRecord(e->ev[1], e->stream));
 
     if (e->n > 0) {
-        if (e->chunks.size() < 2 || e->chunks.back() != e->n)
+        if (e->chunks.size() < 2 || e->chunks.back() != e->n || (!e->chunks_streamed && e->chunks_pool_bound != !uses_fast_path(e)))
             plan_chunks(e, e->h_hit_off.data(), e->h_locus_off.data(), false, 29);
         bool used_slot1 = false;
         for (size_t k = 0; k + 1 < e->chunks.size(); ++k) {
