@@ -131,3 +131,38 @@ def test_chunks_are_contig_aligned(tmp_path):
             names = {r.split(b"\t")[0] for r in raw[off:off + n].split(b"\n") if r}
             assert not names & seen
             seen |= names
+
+
+def test_run_streaming_two_worker_processes(tmp_path):
+    """The whole driver -- chunk queue, two forked workers, results queue, hit-less contigs, merge -- with the stand-in
+    engine; same bytes as the single pass.  An ungrouped blastout is caught across chunks."""
+    import argparse
+    import functools
+    from waafle_b200 import orgscorer
+    data = synth.generate_config("cfg5", n_contigs=120, seed=78, annotations=True)
+    files = data.write_files(str(tmp_path), "s")
+    with open(files["contigs"], "a") as fh:
+        fh.write(">zz_nohits\nACGT\n")
+    flags = dict(weak_loci="penalize")
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir()
+    two.mkdir()
+    single_pass(files, str(one), flags)
+    args = orgscorer.get_args([files["contigs"], files["blastout"], files["gff"], files["taxonomy"], "--outdir", str(two),
+                               "--basename", "run", "--weak-loci", "penalize", "--cpu-parse", "--quiet"])
+    tax = taxonomy.Taxonomy(files["taxonomy"])
+    lengths = read_contig_lengths(files["contigs"])
+    loci = parsers.read_gff_loci(files["gff"])
+    stats, n_chunks = streaming.run_streaming(args, tax, lengths, loci, functools.partial(orgscorer.params_from_args, args),
+                                              [0, 0], os.path.getsize(files["blastout"]) // 9, engine_factory=OracleEngine)
+    assert n_chunks >= 6 and sum(st["chunks"] for k, st in stats.items() if k != "rest") == n_chunks
+    same_outputs(str(one), str(two))
+    assert not [f for f in os.listdir(str(two)) if f.startswith("wfl_shards_")]
+    # the same contig's hits in two places of the file
+    rows = open(files["blastout"]).read().split("\n")
+    with open(files["blastout"], "w") as fh:
+        fh.write("\n".join(rows + rows[:3]))
+    with pytest.raises(SystemExit):
+        streaming.run_streaming(args, taxonomy.Taxonomy(files["taxonomy"]), lengths, loci,
+                                functools.partial(orgscorer.params_from_args, args), [0, 0],
+                                os.path.getsize(files["blastout"]) // 9, engine_factory=OracleEngine)

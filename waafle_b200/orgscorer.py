@@ -148,10 +148,10 @@ def main(argv=None):
             args, tax, contig_lengths, loci, functools.partial(params_from_args, args),
             devices, max(1, chunk_bytes))
         if not args.quiet:
-            for dev in sorted(k for k in stats if k != "rest"):
-                st = stats[dev]
-                say("  cuda:{}: {:,} contigs / {:,} hits in {} chunk(s) ({:.1f} ms in kernels)".format(
-                    dev, st["contigs"], st["hits"], st["chunks"], st["ms_kernels"]))
+            for w in sorted(k for k in stats if k != "rest"):
+                st = stats[w]
+                say("  worker {} on cuda:{}: {:,} contigs / {:,} hits in {} chunk(s) ({:.1f} ms in kernels)".format(
+                    w, st["device"], st["contigs"], st["hits"], st["chunks"], st["ms_kernels"]))
         say("Finished successfully.")
         return
     hits = parsers.read_blast_hits(args.blastout, device=None if args.cpu_parse else args.device)

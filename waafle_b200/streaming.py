@@ -315,9 +315,10 @@ class ChunkScorer:
             self.parser.close()
 
 
-def _worker(device, path, tasks, results, shard_dir, args, tax, contig_lengths, loci_index, params_factory):
+def _worker(wid, device, path, tasks, results, shard_dir, args, tax, contig_lengths, loci_index, params_factory, engine_factory=None):
     try:
-        scorer = ChunkScorer(device, args, tax, contig_lengths, loci_index, params_factory, cpu_parse=args.cpu_parse)
+        scorer = ChunkScorer(device, args, tax, contig_lengths, loci_index, params_factory, cpu_parse=args.cpu_parse,
+                             engine_factory=engine_factory)
         with open(path, "rb") as fh:
             while True:
                 task = tasks.get()
@@ -332,7 +333,7 @@ def _worker(device, path, tasks, results, shard_dir, args, tax, contig_lengths, 
                 prefix = os.path.join(shard_dir, "chunk{:06d}".format(cid))
                 write_shard(records, prefix)
                 results.put(("chunk", cid, prefix, list(scored), None))
-        results.put(("done", device, None, None, scorer.stats))
+        results.put(("done", wid, None, None, dict(scorer.stats, device=device)))
         scorer.close()
     except SystemExit as exc:
         results.put(("error", device, None, None, "worker on cuda:{} exited: {}".format(device, exc)))
@@ -341,8 +342,8 @@ def _worker(device, path, tasks, results, shard_dir, args, tax, contig_lengths, 
         results.put(("error", device, None, None, traceback.format_exc() or repr(exc)))
 
 
-def run_streaming(args, tax, contig_lengths, loci, params_factory, devices, chunk_bytes):
-    """The whole streamed run: returns per-device stats.  `devices`: CUDA device indices, one worker process each.  The
+def run_streaming(args, tax, contig_lengths, loci, params_factory, devices, chunk_bytes, engine_factory=None):
+    """The whole streamed run: returns (per-worker stats keyed by worker index, plus "rest"; number of chunks).  `devices`: CUDA device indices, one worker process each.  The
     CLI's parent process never initialises CUDA before this point, so the workers are plain forks sharing the contig /
     loci tables copy-on-write; a caller that already used CUDA in this process gets spawned workers (pickled tables)."""
     import multiprocessing as mp
@@ -358,14 +359,22 @@ def run_streaming(args, tax, contig_lengths, loci, params_factory, devices, chun
         tasks.put((cid, off, length))
     for _ in devices:
         tasks.put(None)
-    procs = [ctx.Process(target=_worker, args=(d, args.blastout, tasks, results, shard_dir, args, tax, contig_lengths,
-                                               loci_index, params_factory), daemon=True) for d in devices]
+    procs = [ctx.Process(target=_worker, args=(w, d, args.blastout, tasks, results, shard_dir, args, tax, contig_lengths,
+                                               loci_index, params_factory, engine_factory), daemon=True)
+             for w, d in enumerate(devices)]
     for p in procs:
         p.start()
     prefixes, seen, stats, done = {}, set(), {}, 0
     try:
+        import queue
         while done < len(devices):
-            kind, a, b, c, d = results.get()
+            try:
+                kind, a, b, c, d = results.get(timeout=5.0)
+            except queue.Empty:
+                dead = [p for p in procs if not p.is_alive() and p.exitcode not in (0, None)]
+                if dead:   # a worker that died without a word (killed, crashed in native code)
+                    die("streaming worker exited with code {}".format(dead[0].exitcode))
+                continue
             if kind == "error":
                 die(d)
             if kind == "done":
@@ -383,7 +392,8 @@ def run_streaming(args, tax, contig_lengths, loci, params_factory, devices, chun
         # process on the first device -- after the workers are gone
         rest = [nm for nm in contig_lengths if nm not in seen]
         if rest:
-            scorer = ChunkScorer(devices[0], args, tax, contig_lengths, loci_index, params_factory, cpu_parse=True)
+            scorer = ChunkScorer(devices[0], args, tax, contig_lengths, loci_index, params_factory, cpu_parse=True,
+                                 engine_factory=engine_factory)
             empty = parsers.hits_from_columns(*([[]] * 10))
             step = max(1, int(args.chunk_contigs))
             for k in range(0, len(rest), step):
@@ -391,7 +401,7 @@ def run_streaming(args, tax, contig_lengths, loci, params_factory, devices, chun
                 prefix = os.path.join(shard_dir, "rest{:06d}".format(k // step))
                 write_shard(records, prefix)
                 prefixes[len(chunks) + k // step] = prefix
-            stats["rest"] = scorer.stats
+            stats["rest"] = dict(scorer.stats, device=devices[0])
             scorer.close()
         merge_shards([prefixes[k] for k in sorted(prefixes)], args.outdir, args.basename)
     finally:
