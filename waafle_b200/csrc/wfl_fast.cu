@@ -972,8 +972,9 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         bool kept = false;
                         if (t < T && (mk0[t] & um) == um) {
                             const double d = brank - rcache[t];
+                            // (the best option itself has d == 0 exactly: no guard, or --range 0 would trip every contig)
                             if (t != tb && fabs(d) <= GUARD) near = true;
-                            if (P.p.disambiguate_one == 1 && fabs(d - P.p.range) <= GUARD) near = true;
+                            if (t != tb && P.p.disambiguate_one == 1 && fabs(d - P.p.range) <= GUARD) near = true;
                             kept = P.p.disambiguate_one == 1 && d <= P.p.range;
                         }
                         const u32 m = __ballot_sync(FULL, kept);
@@ -1127,7 +1128,7 @@ __global__ void __launch_bounds__(32 * FAST_WPC, WFL_FAST_CPSM) wfl_fast_contigs
                         if (q < nsurv) {
                             const double d = brank - s_rank[q];
                             if (q != bp && fabs(d) <= GUARD) near = true;
-                            if (P.p.disambiguate_two != 0 && fabs(d - P.p.range) <= GUARD) near = true;
+                            if (q != bp && P.p.disambiguate_two != 0 && fabs(d - P.p.range) <= GUARD) near = true;
                             kept = d <= P.p.range;   // :636
                             if (kept) eval_two_fast(L, tax, P, s_a[q], s_b[q], ev);
                         }
