@@ -72,16 +72,27 @@ class Batch:
 
     def sort_hits(self):
         """The same batch with every contig's hits in the order the fused fast-path kernel visits them at the first
-        taxonomy level: by (taxon index, descending waafle_score), ties in file order -- the kernel then only CHECKS the
-        order instead of sorting.  Semantically transparent: envelopes are order-free.  With annotation systems the hits
-        are ordered by descending score alone (ties in file order), so that the annotation tie-break "last hit in file
-        order" (OS:389) stays "largest index among equal scores"; the kernel sorts by clade itself."""
+        taxonomy level: by (taxon index, descending waafle_score) -- the kernel then only CHECKS the order instead of
+        sorting in shared memory.  Semantically transparent: envelopes are order-free.  One stable integer sort of a
+        composite key  contig | taxon | quantised score  (15 M hits/s; np.lexsort on the four columns does 1 M hits/s);
+        scores that collide in the quantisation may stay in file order, which the kernel detects and repairs per contig.
+        With annotation systems the hits stay in FILE order: the annotation tie-break "last hit in file order" (OS:389) is
+        "largest index among equal scores" there, and the kernel sorts by clade itself."""
+        if self.hit_sysmask is not None or self.n_hits == 0:
+            return self
         n = self.n_contigs
         contig = np.repeat(np.arange(n, dtype=np.int64), np.diff(self.hit_off))
-        if self.hit_sysmask is None:
-            order = np.lexsort((np.arange(len(contig)), -self.hit_score, self.hit_taxon, contig))
+        bits_c = max(1, int(n - 1).bit_length())
+        bits_t = max(1, int(self.hit_taxon.max(initial=0)).bit_length())
+        bits_s = 63 - bits_c - bits_t
+        score = np.nan_to_num(self.hit_score, nan=0.0, posinf=0.0, neginf=0.0)
+        smax = float(score.max(initial=0.0))
+        if bits_s >= 20 and smax > 0.0 and int(self.hit_taxon.min(initial=0)) >= 0:
+            q = ((smax - np.clip(score, 0.0, smax)) * (float((1 << bits_s) - 1) / smax)).astype(np.int64)
+            key = (contig << (bits_t + bits_s)) | (self.hit_taxon.astype(np.int64) << bits_s) | q
+            order = np.argsort(key, kind="stable")
         else:
-            order = np.lexsort((np.arange(len(contig)), -self.hit_score, contig))
+            order = np.lexsort((np.arange(len(contig)), -self.hit_score, self.hit_taxon, contig))
         take = lambda a: None if a is None else np.ascontiguousarray(a[order])
         return Batch(
             hit_off=self.hit_off, locus_off=self.locus_off,
