@@ -158,7 +158,7 @@ typedef struct {
     int64_t workspace_retries;  /* contigs replayed by the exact pipeline with a larger workspace */
     int64_t smem_contigs;       /* contigs scored entirely in shared memory by the fused fast-path kernel */
     int64_t fallback_contigs;   /* contigs the fast path handed to the exact pipeline (capacity or guard band) */
-    int64_t second_pass_contigs;/* contigs the first fast pass handed to the second one (larger shared-memory slice) */
+    int64_t second_pass_contigs;/* contigs the first fast pass handed to a retry pass (more survivor pairs / larger slice) */
     int64_t fallback_reasons[8];/* hand-overs of both passes by cause: loci, hits, coordinates, records, clades,
                                    groups, pairs, guard band */
     int64_t guard_trips;        /* ... of which because a rank comparison fell inside the 1e-12 guard band */
@@ -197,8 +197,11 @@ int  wfl_get_stats(const wfl_engine *e, wfl_stats *out);
 /* Tuning / test knobs by name (all optional; defaults are the measured best on B200):
  *   "exact"        1: every contig through the exact pipeline (numpy-pairwise gene scores, bit-exact crit / rank);
  *                  0 (default): fused fast-path kernel with guard bands, exact pipeline for what it hands back
- *   "fast_kcap" / "fast_tcap" / "fast_ncap"   capacities of the fast kernel's shared-memory slice (records per
- *                  locus, clades and groups per level); 0 = choose from the batch
+ *   "fast_hcap" / "fast_tcap" / "fast_ncap"   capacities of the fast kernel's shared-memory slice (staged hit x locus
+ *                  entries per contig, clades and groups per level); 0 = choose from the batch;
+ *                  "fast_hscale_pct" first-pass entry capacity in % of the mean hits per contig (default 160);
+ *                  "fast_passes" 1: no retry passes (overflows go straight to the exact pipeline)
+ *   "details"      capacity of the --write-details dump (wfl_download_details); > 0 implies the exact pipeline
  *   "pool_mb"      workspace pool of the exact pipeline; "chunk_mb" H2D chunk of the plugin call; "streams" 1|2;
  *   "k2_cap"       group-list capacity of the exact pipeline (test hook for its overflow path). */
 int  wfl_set_option(wfl_engine *e, const char *name, int64_t value);
