@@ -23,7 +23,9 @@ def main():
     opts = [x.split("=") for x in a[3:]]
     data = synth.generate_config(workload, n_contigs=n, seed=1000)
     tax = data.taxonomy()
-    batch = data.to_batch(tax).sort_hits()
+    batch = data.to_batch(tax)
+    if os.environ.get("WFL_PROF_UNSORTED") != "1":   # default: what the front end's packer delivers
+        batch = batch.sort_hits()
     P = OrgscorerParams(n_systems=1 if batch.hit_sysmask is not None else 0)
     eng = Engine(0, P, tax)
     for k, v in opts:
