@@ -141,3 +141,28 @@ def test_bad_subject_header_dies_on_both_paths(tmp_path, monkeypatch):
         monkeypatch.setattr(parsers, name, None)
     with pytest.raises(SystemExit):
         parsers.read_blast_hits(str(p))
+
+
+def test_sort_hits_composite_key_equals_lexsort():
+    """packing.Batch.sort_hits: the composite-key integer sort gives the (contig, taxon, descending score, file order)
+    order of np.lexsort; batches with annotation systems stay in file order; taxon indices too wide for the key fall
+    back to lexsort."""
+    import numpy as np
+    from waafle_b200 import synth
+    data = synth.generate_config("cfg2", n_contigs=300, seed=12)
+    tax = data.taxonomy()
+    b = data.to_batch(tax)
+    s = b.sort_hits()
+    contig = np.repeat(np.arange(b.n_contigs), np.diff(b.hit_off))
+    o = np.lexsort((np.arange(len(contig)), -b.hit_score, b.hit_taxon, contig))
+    for k in ("hit_qstart", "hit_qend", "hit_taxon", "hit_score", "hit_scov", "hit_strand"):
+        assert np.array_equal(getattr(s, k), getattr(b, k)[o]), k
+    assert np.array_equal(s.hit_off, b.hit_off)
+    wide = data.to_batch(tax)
+    wide.hit_taxon = (wide.hit_taxon.astype(np.int64) * 400000 % (1 << 31)).astype(np.int32)   # 31-bit taxon indices
+    sw = wide.sort_hits()
+    ow = np.lexsort((np.arange(len(contig)), -wide.hit_score, wide.hit_taxon, contig))
+    assert np.array_equal(sw.hit_score, wide.hit_score[ow]) and np.array_equal(sw.hit_taxon, wide.hit_taxon[ow])
+    ann = synth.generate_config("cfg5", n_contigs=50, seed=13, annotations=True)
+    ba = ann.to_batch(ann.taxonomy())
+    assert ba.sort_hits() is ba
