@@ -195,16 +195,21 @@ def write_shard(records, prefix):
     return systems
 
 
-def _shard_rows(path, n_fixed):
+def _shard_rows(path, n_fixed, all_systems):
+    """(name, row cells) of one shard in name order; the annotation cells are laid out for the run-wide system list."""
     with open(path) as fh:
         head = fh.readline().rstrip("\n")
         systems = head.split(SHARD_SEP) if head else []
+        same = systems == all_systems
         for line in fh:
             parts = line.rstrip("\n").split(SHARD_SEP)
-            name, n_loci = parts[0], int(parts[1])
-            fixed = parts[2:2 + n_fixed]
+            if same:   # the common case: every chunk saw the same systems
+                yield parts[0], parts[2:]
+                continue
+            n_loci = int(parts[1])
             ann = dict(zip(systems, parts[2 + n_fixed:]))
-            yield name, n_loci, fixed, ann
+            missing = writer.format_field("|".join([writer.C_MISSING_ANNOTATION] * n_loci))
+            yield parts[0], parts[2:2 + n_fixed] + [ann.get(s, missing) for s in all_systems]
 
 
 def shard_systems(prefixes):
@@ -224,14 +229,13 @@ def merge_shards(prefixes, outdir, basename, remove=True):
     for opt, fmt in writer.FORMATS.items():
         with open(os.path.join(outdir, ".".join([basename, opt, "tsv"])), "w") as out:
             write_row([k.upper() for k in fmt + [writer.C_ANNOTATION_PREFIX + s for s in systems]], out)
-            streams = [_shard_rows("{}.{}.shard".format(p, opt), len(fmt)) for p in prefixes]
+            streams = [_shard_rows("{}.{}.shard".format(p, opt), len(fmt), systems) for p in prefixes]
             last = None
-            for name, n_loci, fixed, ann in heapq.merge(*streams, key=lambda t: t[0]):
+            for name, cells in heapq.merge(*streams, key=lambda t: t[0]):
                 if name == last:
                     die("blastout is not grouped by query sequence")   # a contig in two chunks
                 last = name
-                missing = writer.format_field("|".join([writer.C_MISSING_ANNOTATION] * n_loci))
-                write_row(fixed + [ann.get(s, missing) for s in systems], out)
+                write_row(cells, out)
     if remove:
         for p in prefixes:
             for opt in writer.FORMATS:
